@@ -1,0 +1,706 @@
+// pa_capi.cu -- implementation of include/pairalign_b200.h: context, sequence
+// store, launch logic and result transfer.  No CPU fallback exists here: every
+// compute entry point needs a CUDA device.
+#include "pa_dp.cuh"
+#include "pa_peak.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+using namespace pa;
+
+constexpr int KFAST = 16;     // columns per lane, 2-bit path
+constexpr int KGEN = 8;       // columns per lane, IUPAC/gap path
+constexpr uint64_t CHUNK_PAIRS = 1ull << 22;   // pairs per launch (84 MB of records)
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(PA_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Device {
+    int id = -1;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // sequence store
+    uint32_t *p2 = nullptr, *p4 = nullptr, *off2 = nullptr, *off4 = nullptr, *len = nullptr;
+    uint8_t *pure = nullptr;
+    // scratch
+    unsigned long long *counters = nullptr;   // [0] fast work counter, [1] general work counter
+    unsigned int *n_deferred = nullptr;
+    uint32_t *deferred = nullptr;
+    size_t deferred_cap = 0;
+    int4 *bbuf = nullptr;
+    uint32_t bbuf_rows = 0;
+    uint32_t n_warps = 0;
+    int grid_fast = 0, grid_gen = 0, grid_stats = 0;
+    pa_pair_result *d_out[2] = {nullptr, nullptr};
+    size_t d_out_cap = 0;
+    pa_pair_result *h_stage[2] = {nullptr, nullptr};
+    uint32_t *d_ia = nullptr, *d_ib = nullptr;
+    size_t d_pairs_cap = 0;
+    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_done[2] = {};
+    // timing accumulators of the last call
+    double fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
+    uint32_t launches = 0;
+};
+
+struct Context {
+    std::vector<Device> dev;
+    // host copy of what partitioning needs
+    uint32_t n_seq = 0;
+    std::vector<uint32_t> len;
+    std::vector<uint64_t> pref;        // pref[s] = sum of len[0..s)
+    std::vector<double> row_cells;     // cells in rows before r (double is exact enough for balancing)
+    std::vector<unsigned __int128> row_cells_exact;
+    bool all_pure = true;
+    uint32_t max_len = 0;
+    pa_timing timing = {};
+};
+
+std::mutex g_mu;
+Context *g_ctx = nullptr;
+
+void free_device(Device &d) {
+    if (d.id < 0) return;
+    cudaSetDevice(d.id);
+    cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
+    cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.bbuf);
+    for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
+    cudaFree(d.d_ia); cudaFree(d.d_ib);
+    for (auto &e : d.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : d.ev_done) if (e) cudaEventDestroy(e);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    d = Device();
+}
+
+SeqStore store_of(const Device &d, uint32_t n_seq) {
+    SeqStore s;
+    s.p2 = d.p2; s.p4 = d.p4; s.off2 = d.off2; s.off4 = d.off4; s.len = d.len; s.pure = d.pure; s.n_seq = n_seq;
+    return s;
+}
+
+// The PRMT byte tables need every score (and score+GO) to fit a signed byte and
+// the pad fixed point needs GO <= 0, GE <= 0; anything else runs on the general kernel.
+bool fast_params_ok(const pa_params &p) {
+    auto fits = [](long long v) { return v >= -128 && v <= 127; };
+    return p.gap_open <= 0 && p.gap_ext <= 0 && p.gap_open >= -127 && fits(p.match) && fits(p.mismatch) &&
+           fits((long long)p.match + p.gap_open) && fits((long long)p.mismatch + p.gap_open);
+}
+
+// cells of all pairs with triangle index < q
+unsigned __int128 cells_before(const Context &c, uint64_t q) {
+    const uint64_t N = c.n_seq;
+    if (N < 2) return 0;
+    const uint64_t total = N * (N - 1) / 2;
+    if (q >= total) return c.row_cells_exact[N - 1];
+    uint32_t a, b;
+    tri_pair(q, (uint32_t)N, a, b);
+    return c.row_cells_exact[a] + (unsigned __int128)c.len[a] * (c.pref[b] - c.pref[a + 1]);
+}
+
+int ensure_out(Device &d, size_t n) {
+    if (n <= d.d_out_cap) return PA_OK;
+    for (int k = 0; k < 2; ++k) {
+        if (d.d_out[k]) cudaFree(d.d_out[k]);
+        if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]);
+        d.d_out[k] = nullptr; d.h_stage[k] = nullptr;
+    }
+    d.d_out_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaMalloc(&d.d_out[k], n * sizeof(pa_pair_result)));
+        CU(cudaMallocHost(&d.h_stage[k], n * sizeof(pa_pair_result)));
+    }
+    d.d_out_cap = n;
+    return PA_OK;
+}
+
+int ensure_deferred(Device &d, size_t n) {
+    if (n <= d.deferred_cap) return PA_OK;
+    if (d.deferred) cudaFree(d.deferred);
+    d.deferred = nullptr; d.deferred_cap = 0;
+    CU(cudaMalloc(&d.deferred, n * sizeof(uint32_t)));
+    d.deferred_cap = n;
+    return PA_OK;
+}
+
+// The general kernel reads its item count from device memory (n_deferred), so
+// no host round trip sits between the two launches.
+template <int K>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_general_deferred_kernel(const SeqStore S, const Scoring sc, PairSource src, const unsigned int *n_items,
+                           unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
+                           pa_pair_result *out) {
+    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    const unsigned long long count = *n_items;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1ull);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= count) break;
+        const uint64_t e = src.idx[w];
+        uint32_t a, b;
+        if (src.ia) { a = src.ia[e]; b = src.ib[e]; }
+        else tri_pair(src.first + e, S.n_seq, a, b);
+        const int n = (int)S.len[a], m = (int)S.len[b];
+        __syncwarp();
+        const uint32_t *xs = stage_seq(S.p4 + S.off4[a], (uint32_t)(n + 7) >> 3, stage[wib][0], lane);
+        const uint32_t *ys = stage_seq(S.p4 + S.off4[b], (uint32_t)(m + 7) >> 3, stage[wib][1], lane);
+        __syncwarp();
+        align_warp<K, true>(xs, n, ys, m, sc, bbuf, &out[e], lane);
+    }
+}
+
+// Launch the kernels for `count` elements (triangle range starting at `first`,
+// or the explicit lists ia/ib) writing records to d_out (device).  Asynchronous
+// on d.stream; events ev[0..3] bracket the two DP kernels.
+int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
+                 const uint32_t *d_ia, const uint32_t *d_ib, pa_pair_result *d_out) {
+    const SeqStore S = store_of(d, c.n_seq);
+    Scoring sc{p.match, p.mismatch, p.gap_open, p.gap_ext};
+    PairSource src{first, d_ia, d_ib, nullptr};
+    CU(cudaMemsetAsync(d.counters, 0, 2 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.n_deferred, 0, sizeof(unsigned int), d.stream));
+    if (p.aligned) {
+        CU(cudaEventRecord(d.ev[0], d.stream));
+        pa_aligned_stats_kernel<<<d.grid_stats, WARPS_PER_CTA * 32, 0, d.stream>>>(S, src, count, d.counters, d_out);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(d.ev[1], d.stream));
+        CU(cudaEventRecord(d.ev[2], d.stream));
+        CU(cudaEventRecord(d.ev[3], d.stream));
+        d.launches += 1;
+        return PA_OK;
+    }
+    const bool fast = fast_params_ok(p);
+    int rc = ensure_deferred(d, (size_t)count);
+    if (rc) return rc;
+    CU(cudaEventRecord(d.ev[0], d.stream));
+    if (fast) {
+        pa_warp_dp_kernel<KFAST, false><<<d.grid_fast, WARPS_PER_CTA * 32, 0, d.stream>>>(
+            S, sc, src, count, d.counters, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
+        CU(cudaGetLastError());
+        d.launches += 1;
+    }
+    CU(cudaEventRecord(d.ev[1], d.stream));
+    CU(cudaEventRecord(d.ev[2], d.stream));
+    if (!fast) {
+        pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, WARPS_PER_CTA * 32, 0, d.stream>>>(
+            S, sc, src, count, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
+        CU(cudaGetLastError());
+        d.launches += 1;
+    } else if (!c.all_pure) {
+        PairSource s2 = src;
+        s2.idx = d.deferred;
+        pa_general_deferred_kernel<KGEN><<<d.grid_gen, WARPS_PER_CTA * 32, 0, d.stream>>>(
+            S, sc, s2, d.n_deferred, d.counters + 1, d.bbuf, d.bbuf_rows, d_out);
+        CU(cudaGetLastError());
+        d.launches += 1;
+    }
+    CU(cudaEventRecord(d.ev[3], d.stream));
+    return PA_OK;
+}
+
+int collect_chunk_times(Device &d) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+    d.fast_ms += ms;
+    CU(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]));
+    d.gen_ms += ms;
+    return PA_OK;
+}
+
+// Run one device's share [first, first+count) of the triangle (or of the
+// explicit lists) and deliver records to host memory `out` (out[0] is element
+// `first`).  Chunks are double-buffered: the kernel of chunk k+1 runs while
+// chunk k travels to the host and is copied into the caller's buffer.
+int run_range(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
+              const uint32_t *h_ia, const uint32_t *h_ib, pa_pair_result *out, pa_pair_result *d_resident) {
+    CU(cudaSetDevice(d.id));
+    d.fast_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
+    d.launches = 0;
+    if (count == 0) return PA_OK;
+    const uint64_t chunk = std::min<uint64_t>(CHUNK_PAIRS, count);
+    int rc;
+    if (!d_resident) { rc = ensure_out(d, (size_t)chunk); if (rc) return rc; }
+    if (h_ia) {
+        if (count > d.d_pairs_cap) {
+            cudaFree(d.d_ia); cudaFree(d.d_ib); d.d_ia = d.d_ib = nullptr; d.d_pairs_cap = 0;
+            CU(cudaMalloc(&d.d_ia, count * sizeof(uint32_t)));
+            CU(cudaMalloc(&d.d_ib, count * sizeof(uint32_t)));
+            d.d_pairs_cap = count;
+        }
+        CU(cudaEventRecord(d.ev[4], d.stream));
+        CU(cudaMemcpyAsync(d.d_ia, h_ia, count * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.d_ib, h_ib, count * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaEventRecord(d.ev[5], d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]));
+        d.h2d_ms += ms;
+    }
+    uint64_t done = 0;
+    int slot = 0;
+    struct Pending { bool active = false; uint64_t off = 0, n = 0; } pend[2];
+    auto drain = [&](int s) -> int {
+        if (!pend[s].active) return PA_OK;
+        CU(cudaEventSynchronize(d.ev_done[s]));
+        memcpy(out + pend[s].off, d.h_stage[s], pend[s].n * sizeof(pa_pair_result));
+        pend[s].active = false;
+        return PA_OK;
+    };
+    while (done < count) {
+        const uint64_t nthis = std::min<uint64_t>(chunk, count - done);
+        pa_pair_result *dst = d_resident ? d_resident + done : d.d_out[slot];
+        if (!d_resident) { rc = drain(slot); if (rc) return rc; }
+        rc = launch_chunk(c, d, p, first + done, nthis, h_ia ? d.d_ia + done : nullptr, h_ia ? d.d_ib + done : nullptr, dst);
+        if (rc) return rc;
+        if (!d_resident) {
+            // copy on the same stream (ordered after the kernels); the host memcpy of
+            // the previous chunk overlaps the next kernel
+            CU(cudaMemcpyAsync(d.h_stage[slot], dst, nthis * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaEventRecord(d.ev_done[slot], d.stream));
+            pend[slot].active = true; pend[slot].off = done; pend[slot].n = nthis;
+        }
+        // kernel events of this chunk are reused by the next launch: wait for them
+        CU(cudaEventSynchronize(d.ev[3]));
+        rc = collect_chunk_times(d);
+        if (rc) return rc;
+        if (!d_resident) {
+            float ms = 0;
+            CU(cudaEventSynchronize(d.ev_done[slot]));
+            CU(cudaEventElapsedTime(&ms, d.ev[3], d.ev_done[slot]));
+            d.d2h_ms += ms;
+        }
+        done += nthis;
+        slot ^= 1;
+    }
+    if (!d_resident) { rc = drain(0); if (rc) return rc; rc = drain(1); if (rc) return rc; }
+    CU(cudaStreamSynchronize(d.stream));
+    return PA_OK;
+}
+
+int check_params(const pa_params *p) {
+    if (!p) return fail(PA_EINVAL, "params is NULL");
+    return PA_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+int pa_api_version(void) { return PA_API_VERSION; }
+const char *pa_last_error(void) { return g_err.c_str(); }
+
+int pa_init(const int *devices, int n_dev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx) { for (auto &d : g_ctx->dev) free_device(d); delete g_ctx; g_ctx = nullptr; }
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail <= 0)
+        return fail(PA_ENODEVICE, "no CUDA device available (%s); pairalign_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> ids;
+    if (!devices || n_dev <= 0) ids.push_back(0);
+    else for (int k = 0; k < n_dev; ++k) ids.push_back(devices[k]);
+    Context *c = new Context();
+    for (int id : ids) {
+        if (id < 0 || id >= avail) { delete c; return fail(PA_EINVAL, "device %d out of range (0..%d)", id, avail - 1); }
+        Device d;
+        d.id = id;
+        cudaDeviceProp prop;
+        if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess) {
+            delete c; return fail(PA_ECUDA, "cannot select device %d", id);
+        }
+        if (prop.major < 10) { delete c; return fail(PA_ENODEVICE, "device %d is sm_%d%d; this module is built for sm_100a only", id, prop.major, prop.minor); }
+        d.n_sm = prop.multiProcessorCount;
+        c->dev.push_back(d);
+    }
+    for (auto &d : c->dev) {
+        cudaSetDevice(d.id);
+        cudaError_t e2 = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
+        for (auto &ev : d.ev) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
+        for (auto &ev : d.ev_done) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 2 * sizeof(unsigned long long));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, sizeof(unsigned int));
+        int occ = 0;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KFAST, false>, WARPS_PER_CTA * 32, 0);
+        d.grid_fast = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
+        d.grid_gen = std::max(1, occ) * d.n_sm;
+        int occ2 = 0;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pa_general_deferred_kernel<KGEN>, WARPS_PER_CTA * 32, 0);
+        d.grid_gen = std::min(d.grid_gen, std::max(1, occ2) * d.n_sm);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
+        d.grid_stats = std::max(1, occ) * d.n_sm;
+        d.n_warps = (uint32_t)std::max(d.grid_fast, d.grid_gen) * WARPS_PER_CTA;
+        if (e2 != cudaSuccess) {
+            std::string msg = cudaGetErrorString(e2);
+            for (auto &dd : c->dev) free_device(dd);
+            delete c;
+            return fail(PA_ECUDA, "device %d setup failed: %s", d.id, msg.c_str());
+        }
+    }
+    g_ctx = c;
+    return PA_OK;
+}
+
+void pa_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return;
+    for (auto &d : g_ctx->dev) free_device(d);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+int pa_device_count(void) { return g_ctx ? (int)g_ctx->dev.size() : 0; }
+
+// ---- front end --------------------------------------------------------------
+int pa_char_to_mask(unsigned char ch) {
+    // bit0 A, bit1 G, bit2 C, bit3 T; unions for the IUPAC codes; '-' empty; N and '.' everything
+    static int8_t tab[256];
+    static bool init = false;
+    if (!init) {
+        for (int k = 0; k < 256; ++k) tab[k] = -2;
+        tab[' '] = tab['\n'] = tab['\r'] = tab['\t'] = -1;
+        const char *codes = "-AGRCMSVTWKDYHBN";   // index = bit set
+        for (int v = 0; v < 16; ++v) {
+            tab[(unsigned char)codes[v]] = (int8_t)v;
+            if (codes[v] >= 'A' && codes[v] <= 'Z') tab[(unsigned char)(codes[v] - 'A' + 'a')] = (int8_t)v;
+        }
+        tab['.'] = 15;
+        init = true;
+    }
+    return tab[ch];
+}
+
+char pa_mask_to_char(uint8_t mask) {
+    // ascending char order in the reference's map puts '-' before letters and '.' before 'N'
+    static const char codes[17] = "-AGRCMSVTWKDYHB.";
+    return codes[mask & 15];
+}
+
+size_t pa_encode_sequence(const char *text, size_t len, uint8_t *out, size_t *n_unknown,
+                          char *unknown_chars, size_t unknown_cap) {
+    size_t n = 0, unk = 0;
+    for (size_t k = 1; k < len; ++k) {
+        const int v = pa_char_to_mask((unsigned char)text[k]);
+        if (v >= 0) out[n++] = (uint8_t)v;
+        else if (v == -2) { if (unknown_chars && unk < unknown_cap) unknown_chars[unk] = text[k]; ++unk; }
+    }
+    if (n_unknown) *n_unknown = unk;
+    return n;
+}
+
+int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t n_seq) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (!offsets || (!masks && n_seq && offsets[n_seq] > 0)) return fail(PA_EINVAL, "NULL sequence buffer");
+    Context &c = *g_ctx;
+    std::vector<uint32_t> len(n_seq), off2(n_seq), off4(n_seq);
+    std::vector<uint8_t> pure(n_seq);
+    uint64_t w2 = 0, w4 = 0;
+    uint32_t max_len = 0;
+    bool all_pure = true;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        if (offsets[s + 1] < offsets[s]) return fail(PA_EINVAL, "offsets not ascending at %u", s);
+        const uint64_t L = offsets[s + 1] - offsets[s];
+        if (L > PA_MAX_SEQ_LEN) return fail(PA_ERANGE, "sequence %u has %llu bases (max %u)", s, (unsigned long long)L, PA_MAX_SEQ_LEN);
+        len[s] = (uint32_t)L;
+        max_len = std::max(max_len, len[s]);
+        off2[s] = (uint32_t)w2; off4[s] = (uint32_t)w4;
+        w2 += ((L + 15) / 16 + 3) / 4 * 4;     // whole 16-byte units
+        w4 += ((L + 7) / 8 + 3) / 4 * 4;
+        if (w4 > 0xffffffffull) return fail(PA_ERANGE, "sequence set too large");
+    }
+    std::vector<uint32_t> p2(std::max<uint64_t>(w2, 4), 0), p4(std::max<uint64_t>(w4, 4), 0);
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        const uint8_t *src = masks + offsets[s];
+        bool pr = true;
+        for (uint32_t k = 0; k < len[s]; ++k) {
+            const uint32_t v = src[k] & 15u;
+            p4[off4[s] + (k >> 3)] |= v << ((k & 7) * 4);
+            uint32_t code = 0;
+            switch (v) { case 1: code = 0; break; case 2: code = 1; break; case 4: code = 2; break; case 8: code = 3; break; default: pr = false; }
+            p2[off2[s] + (k >> 4)] |= code << ((k & 15) * 2);
+        }
+        pure[s] = pr ? 1 : 0;
+        all_pure = all_pure && pr;
+    }
+    c.n_seq = n_seq;
+    c.len = len;
+    c.max_len = max_len;
+    c.all_pure = all_pure;
+    c.pref.assign((size_t)n_seq + 1, 0);
+    for (uint32_t s = 0; s < n_seq; ++s) c.pref[s + 1] = c.pref[s] + len[s];
+    c.row_cells_exact.assign((size_t)n_seq + 1, 0);
+    for (uint32_t r = 0; r + 1 < n_seq; ++r)
+        c.row_cells_exact[r + 1] = c.row_cells_exact[r] + (unsigned __int128)len[r] * (c.pref[n_seq] - c.pref[r + 1]);
+    if (n_seq) c.row_cells_exact[n_seq] = c.row_cells_exact[n_seq - 1];
+
+    for (auto &d : c.dev) {
+        CU(cudaSetDevice(d.id));
+        cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure); cudaFree(d.bbuf);
+        d.p2 = d.p4 = d.off2 = d.off4 = d.len = nullptr; d.pure = nullptr; d.bbuf = nullptr;
+        CU(cudaMalloc(&d.p2, p2.size() * 4));
+        CU(cudaMalloc(&d.p4, p4.size() * 4));
+        CU(cudaMalloc(&d.off2, std::max<size_t>(n_seq, 1) * 4));
+        CU(cudaMalloc(&d.off4, std::max<size_t>(n_seq, 1) * 4));
+        CU(cudaMalloc(&d.len, std::max<size_t>(n_seq, 1) * 4));
+        CU(cudaMalloc(&d.pure, std::max<size_t>(n_seq, 1)));
+        CU(cudaMemcpy(d.p2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.p4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice));
+        if (n_seq) {
+            CU(cudaMemcpy(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice));
+        }
+        d.bbuf_rows = std::max<uint32_t>(max_len, 1);
+        CU(cudaMalloc(&d.bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
+    }
+    return PA_OK;
+}
+
+uint32_t pa_num_sequences(void) { return g_ctx ? g_ctx->n_seq : 0; }
+
+uint64_t pa_num_pairs(void) {
+    if (!g_ctx) return 0;
+    const uint64_t n = g_ctx->n_seq;
+    return n < 2 ? 0 : n * (n - 1) / 2;
+}
+
+int pa_pair_from_index(uint64_t k, uint32_t *a, uint32_t *b) {
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (k >= pa_num_pairs() || !a || !b) return fail(PA_EINVAL, "pair index out of range");
+    tri_pair(k, g_ctx->n_seq, *a, *b);
+    return PA_OK;
+}
+
+uint64_t pa_count_cells(uint64_t first, uint64_t count) {
+    if (!g_ctx) return 0;
+    const uint64_t total = pa_num_pairs();
+    if (first > total) first = total;
+    if (count > total - first) count = total - first;
+    return (uint64_t)(cells_before(*g_ctx, first + count) - cells_before(*g_ctx, first));
+}
+
+int pa_partition_pairs(uint64_t first, uint64_t count, uint32_t n_parts, uint64_t *bounds) {
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (!bounds || n_parts == 0) return fail(PA_EINVAL, "bad partition arguments");
+    const uint64_t total = pa_num_pairs();
+    if (first > total || count > total - first) return fail(PA_ERANGE, "pair range outside the triangle");
+    const Context &c = *g_ctx;
+    const unsigned __int128 lo = cells_before(c, first), hi = cells_before(c, first + count);
+    bounds[0] = first;
+    for (uint32_t p = 1; p < n_parts; ++p) {
+        const unsigned __int128 target = lo + (hi - lo) * p / n_parts;
+        uint64_t a = bounds[p - 1], b = first + count;     // smallest q in [a,b] with cells_before(q) >= target
+        while (a < b) {
+            const uint64_t mid = a + (b - a) / 2;
+            if (cells_before(c, mid) >= target) b = mid; else a = mid + 1;
+        }
+        bounds[p] = a;
+    }
+    bounds[n_parts] = first + count;
+    return PA_OK;
+}
+
+static int align_impl(const pa_params *params, uint64_t first, uint64_t count, const uint32_t *ia, const uint32_t *ib,
+                      pa_pair_result *out, pa_pair_result *d_resident) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    int rc = check_params(params);
+    if (rc) return rc;
+    Context &c = *g_ctx;
+    if (!c.dev[0].p4) return fail(PA_EINVAL, "no sequences uploaded");
+    if (!out && !d_resident && count) return fail(PA_EINVAL, "NULL result buffer");
+    if (!ia) {
+        const uint64_t total = pa_num_pairs();
+        if (first > total || count > total - first) return fail(PA_ERANGE, "pair range outside the triangle");
+    } else {
+        for (uint64_t k = 0; k < count; ++k)
+            if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t nd = d_resident ? 1 : c.dev.size();
+    std::vector<uint64_t> bounds(nd + 1);
+    if (!ia) {
+        if (nd == 1) { bounds[0] = first; bounds[1] = first + count; }
+        else {
+            const unsigned __int128 lo = cells_before(c, first), hi = cells_before(c, first + count);
+            bounds[0] = first;
+            for (size_t p = 1; p < nd; ++p) {
+                const unsigned __int128 target = lo + (hi - lo) * p / nd;
+                uint64_t a = bounds[p - 1], b = first + count;
+                while (a < b) { const uint64_t mid = a + (b - a) / 2; if (cells_before(c, mid) >= target) b = mid; else a = mid + 1; }
+                bounds[p] = a;
+            }
+            bounds[nd] = first + count;
+        }
+    } else {
+        for (size_t p = 0; p <= nd; ++p) bounds[p] = count * p / nd;
+    }
+    std::vector<int> rcs(nd, PA_OK);
+    std::vector<std::string> errs(nd);
+    auto work = [&](size_t p) {
+        const uint64_t lo = bounds[p], n = bounds[p + 1] - bounds[p];
+        if (!ia) rcs[p] = run_range(c, c.dev[p], *params, lo, n, nullptr, nullptr, out ? out + (lo - first) : nullptr, d_resident);
+        else rcs[p] = run_range(c, c.dev[p], *params, 0, n, ia + lo, ib + lo, out + lo, nullptr);
+        if (rcs[p]) errs[p] = g_err;
+    };
+    if (nd == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t p = 0; p < nd; ++p) th.emplace_back(work, p);
+        for (auto &t : th) t.join();
+    }
+    for (size_t p = 0; p < nd; ++p) if (rcs[p]) { g_err = errs[p]; return rcs[p]; }
+    const auto t1 = std::chrono::steady_clock::now();
+    pa_timing &tm = c.timing;
+    tm = pa_timing();
+    for (size_t p = 0; p < nd; ++p) {
+        const Device &d = c.dev[p];
+        tm.kernel_ms = std::max(tm.kernel_ms, d.fast_ms + d.gen_ms);
+        tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
+        tm.dp_general_ms = std::max(tm.dp_general_ms, d.gen_ms);
+        tm.d2h_ms = std::max(tm.d2h_ms, d.d2h_ms);
+        tm.h2d_ms = std::max(tm.h2d_ms, d.h2d_ms);
+        tm.kernel_launches += d.launches;
+    }
+    tm.total_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    tm.pairs = count;
+    tm.n_devices = (uint32_t)nd;
+    if (!ia) tm.cells = (uint64_t)(cells_before(c, first + count) - cells_before(c, first));
+    else { uint64_t cells = 0; for (uint64_t k = 0; k < count; ++k) cells += (uint64_t)c.len[ia[k]] * c.len[ib[k]]; tm.cells = cells; }
+    return PA_OK;
+}
+
+int pa_align_all_pairs(const pa_params *params, uint64_t first, uint64_t count, pa_pair_result *out) {
+    return align_impl(params, first, count, nullptr, nullptr, out, nullptr);
+}
+
+int pa_align_pairs(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count, pa_pair_result *out) {
+    if (count && (!ia || !ib)) return fail(PA_EINVAL, "NULL pair list");
+    if (count == 0) return PA_OK;
+    return align_impl(params, 0, count, ia, ib, out, nullptr);
+}
+
+int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t count, void *d_out) {
+    if (!d_out && count) return fail(PA_EINVAL, "NULL device buffer");
+    return align_impl(params, first, count, nullptr, nullptr, nullptr, (pa_pair_result *)d_out);
+}
+
+int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b, uint8_t *ax, uint8_t *ay, uint32_t cap,
+                            uint32_t *alen, pa_pair_result *res) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    int rc = check_params(params);
+    if (rc) return rc;
+    Context &c = *g_ctx;
+    if (a >= c.n_seq || b >= c.n_seq) return fail(PA_ERANGE, "sequence index out of range");
+    if (!ax || !ay || !alen) return fail(PA_EINVAL, "NULL output buffer");
+    const uint32_t n = c.len[a], m = c.len[b];
+    if (cap < n + m) return fail(PA_EINVAL, "alignment buffers need n+m = %u bytes", n + m);
+    if (n == 0 || m == 0) return fail(PA_EINVAL, "empty sequence: the reference's behaviour is undefined here");
+    Device &d = c.dev[0];
+    CU(cudaSetDevice(d.id));
+    uint8_t *dirs = nullptr, *rx = nullptr, *ry = nullptr;
+    uint32_t *d_alen = nullptr;
+    pa_pair_result *d_res = nullptr;
+    const size_t cells = (size_t)n * m;
+    cudaError_t e = cudaMalloc(&dirs, cells);
+    if (e == cudaSuccess) e = cudaMalloc(&rx, (size_t)n + m);
+    if (e == cudaSuccess) e = cudaMalloc(&ry, (size_t)n + m);
+    if (e == cudaSuccess) e = cudaMalloc(&d_alen, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(pa_pair_result));
+    pa_pair_result hres;
+    uint32_t halen = 0;
+    std::vector<uint8_t> hx((size_t)n + m), hy((size_t)n + m);
+    if (e == cudaSuccess) {
+        Scoring sc{params->match, params->mismatch, params->gap_open, params->gap_ext};
+        pa_traceback_kernel<KGEN><<<1, 32, 0, d.stream>>>(store_of(d, c.n_seq), sc, a, b, d.bbuf, dirs, d_res, rx, ry, d_alen);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = cudaMemcpy(&halen, d_alen, sizeof halen, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&hres, d_res, sizeof hres, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && halen <= n + m) {
+        e = cudaMemcpy(hx.data(), rx, halen, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hy.data(), ry, halen, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dirs); cudaFree(rx); cudaFree(ry); cudaFree(d_alen); cudaFree(d_res);
+    if (e != cudaSuccess) return fail(PA_ECUDA, "traceback failed: %s", cudaGetErrorString(e));
+    if (halen > n + m) return fail(PA_ECUDA, "traceback produced %u columns for n+m=%u", halen, n + m);
+    for (uint32_t k = 0; k < halen; ++k) { ax[k] = hx[halen - 1 - k]; ay[k] = hy[halen - 1 - k]; }   // src/seqpair.cpp:183-188
+    *alen = halen;
+    if (res) *res = hres;
+    return PA_OK;
+}
+
+int pa_get_timing(pa_timing *t) {
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (!t) return fail(PA_EINVAL, "NULL timing");
+    *t = g_ctx->timing;
+    return PA_OK;
+}
+
+// ---- statistics: the reference's expressions, evaluated by the host's libm ----
+double pa_similarity(uint32_t dist, uint32_t len) {
+    if (len > 0) return 1.0 - ((int)dist / double((int)len));
+    return 1.0;
+}
+double pa_pdistance(uint32_t dist, uint32_t len) { return 1 - pa_similarity(dist, len); }
+double pa_jc_distance(uint32_t dist, uint32_t len) {
+    const double p = 1 - pa_similarity(dist, len);
+    return log(1.0 - (4.0 / 3.0) * p) * (-3.0 / 4.0);
+}
+double pa_jc_minus_p(uint32_t dist, uint32_t len) { return pa_jc_distance(dist, len) - (1.0 - pa_similarity(dist, len)); }
+
+int pa_int32_peak(int which, double *gops, double *sm_mhz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (!gops) return fail(PA_EINVAL, "NULL output");
+    Device &d = g_ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    double g = 0, mhz = 0;
+    cudaError_t e = pa::run_peak(which, d.n_sm, d.stream, &g, &mhz);
+    if (e == cudaErrorInvalidValue) return fail(PA_EINVAL, "unknown instruction class %d", which);
+    if (e != cudaSuccess) return fail(PA_ECUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+    *gops = g;
+    if (sm_mhz) *sm_mhz = mhz;
+    return PA_OK;
+}
+
+}  // extern "C"

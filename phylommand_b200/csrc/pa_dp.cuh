@@ -1,0 +1,418 @@
+// pa_dp.cuh -- device code of the pairalign hot path for sm_100a.
+//
+// What the reference computes per pair (all citations relative to the
+// reference checkout): seqpair::align() fills three n x m int matrices
+// (src/seqpair.cpp:95-131), picks the best cell of the last column / last row
+// (src/seqpair.cpp:134-143), walks back re-deciding the move at every cell from
+// the three values AT that cell (src/seqpair.cpp:159-178), and then
+// hamming_distance()/similarity() count columns over the aligned strings
+// (src/seqpair.cpp:238-274).
+//
+// How it is computed here: nothing is stored.  Because the move at (i,j)
+// depends only on (H,Gy,Gx) at (i,j), every cell has exactly one predecessor
+// and the pair (compared columns, mismatching columns) of the reference's
+// traceback path ending in (i,j) obeys the same dependency pattern as the
+// scores.  One warp owns one pair; each lane keeps a strip of K columns in
+// registers and the warp sweeps the rows as a skewed wavefront (lane l works
+// on row t-l at step t), passing the strip's right edge to lane l+1 with
+// __shfl_up_sync.  Sequences wider than 32*K columns take several passes; the
+// right edge of a pass goes through a per-warp scratch row in global memory
+// (16 B per row, L2 resident).
+//
+// Recurrence (0-based, i over x = rows, j over y = columns):
+//   H (i,j) = max(H(i-1,j-1), Gy(i-1,j), Gx(i,j-1)) + s(i,j)
+//   Gy(i,j) = max(H(i-1,j-1)+GO, Gy(i-1,j)+GE)
+//   Gx(i,j) = max(H(i-1,j-1)+GO, Gx(i,j-1)+GE)
+//   first row / column: H = s, Gy = Gx = 0            (src/seqpair.cpp:103-120)
+//   move(i,j) = D if H>=Gy && H>=Gx, else U if Gy>=Gx, else L
+//   cnt(i,j)  = D ? cnt(i-1,j-1)+[both non-gap](1 column, mismatch?) :
+//               U ? cnt(i-1,j) : cnt(i,j-1);   cnt = 0 outside the matrix
+// cnt packs (columns << 16 | mismatches).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+#include "../../include/pairalign_b200.h"
+
+namespace pa {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int WARPS_PER_CTA = 4;
+constexpr int STAGE_WORDS = 256;     // per sequence per warp: 1 KB = 4096 2-bit or 2048 4-bit codes
+
+struct SeqStore {
+    const uint32_t *p2;      // 2 bit/base (A0 G1 C2 T3), 16 bases per word, every sequence 16-byte aligned
+    const uint32_t *p4;      // 4 bit/base IUPAC sets, 8 bases per word, every sequence 16-byte aligned
+    const uint32_t *off2;    // word offset of sequence s in p2
+    const uint32_t *off4;    // word offset of sequence s in p4
+    const uint32_t *len;     // encoded length
+    const uint8_t  *pure;    // 1 if the sequence holds only A/C/G/T
+    uint32_t n_seq;
+};
+
+struct Scoring { int match, mismatch, go, ge; };
+
+struct PairSource {
+    uint64_t first;          // triangle mode: global index of element 0
+    const uint32_t *ia;      // explicit mode (ia != nullptr): pair k = (ia[k], ib[k])
+    const uint32_t *ib;
+    const uint32_t *idx;     // optional indirection: work item w handles element idx[w]
+};
+
+// Row-major upper-triangle index -> (a,b), a<b.  Rows before r hold
+// r*(2N-r-1)/2 pairs.
+__host__ __device__ inline uint64_t tri_row_start(uint64_t r, uint64_t N) { return r * (2 * N - r - 1) / 2; }
+
+__host__ __device__ inline void tri_pair(uint64_t q, uint32_t N, uint32_t &a, uint32_t &b) {
+    const double t = 2.0 * (double)N - 1.0;
+    double disc = t * t - 8.0 * (double)q;
+    if (disc < 0.0) disc = 0.0;
+    long long r = (long long)((t - sqrt(disc)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > (long long)N - 2) r = (long long)N - 2;
+    while (r > 0 && tri_row_start((uint64_t)r, N) > q) --r;
+    while (r < (long long)N - 2 && tri_row_start((uint64_t)r + 1, N) <= q) ++r;
+    a = (uint32_t)r;
+    b = (uint32_t)(r + 1 + (long long)(q - tri_row_start((uint64_t)r, N)));
+}
+
+__device__ __forceinline__ uint32_t fetch2(const uint32_t *w, int j) { return (w[j >> 4] >> ((j & 15) * 2)) & 3u; }
+__device__ __forceinline__ uint32_t fetch4(const uint32_t *w, int j) { return (w[j >> 3] >> ((j & 7) * 4)) & 15u; }
+
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+
+// prmt.b32 in its default mode: selector nibble bits 0-2 pick one of the 8
+// source bytes (a: 0-3, b: 4-7); bit 3 replicates that byte's sign bit instead.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// One pair on one warp.  xs/ys: packed codes (2-bit when !GENERAL, 4-bit sets
+// when GENERAL), generic pointers (shared staging or global).
+//
+// Column layout: the m columns are RIGHT-aligned in P*32*K slots, so the last
+// column is always the last slot of lane 31 in the last pass and its per-row
+// values are exactly what that lane hands on anyway.  The padL = P*32*K-m slots
+// before column 0 are neutral pad columns:
+//   !GENERAL: pad cells score 0 and count nothing; with the virtual values
+//     H=-GO, Gy=Gx=0 that is a fixed point of the recurrence, and -GO is what
+//     column 0 / row 0 need to see so that (with GO added to their scores)
+//     H = s and Gy = Gx = 0 come out of the ordinary recurrence: no per-cell
+//     boundary test.  Scores come from two byte tables indexed with PRMT.
+//   GENERAL: explicit flags per column (any parameters, gaps -> INT_MIN with
+//     32-bit wrap-around exactly as the reference binary behaves).
+// ---------------------------------------------------------------------------
+template <int K, bool GENERAL, bool DIRS = false>
+__device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, const uint32_t *ys, const int m,
+                                           const Scoring sc, int4 *bbuf, pa_pair_result *res, const int lane,
+                                           uint8_t *dirs = nullptr) {
+    constexpr int W = 32 * K;
+    const int P = (m + W - 1) / W;
+    const int padL = P * W - m;
+    const int Hinit = GENERAL ? 0 : -sc.go;
+
+    int rowBest = INT_MIN, rowJ = 0;
+    uint32_t rowC = 0;
+    int colBest = INT_MIN, colI = 0;
+    uint32_t colC = 0;
+
+    // fast-path constants
+    uint32_t y0 = 0, baseN = 0, baseZ = 0, dN = 0, dZ = 0, c0m = 0, c0x = 0;
+    if (!GENERAL) {
+        y0 = fetch2(ys, 0);
+        const uint32_t Mn = (uint32_t)sc.match & 0xffu, Xn = (uint32_t)sc.mismatch & 0xffu;
+        const uint32_t Mz = (uint32_t)(sc.match + sc.go) & 0xffu, Xz = (uint32_t)(sc.mismatch + sc.go) & 0xffu;
+        baseN = Xn * 0x01010101u; dN = Mn ^ Xn;
+        baseZ = Xz * 0x01010101u; dZ = Mz ^ Xz;
+        c0m = Mz; c0x = Xz;
+    }
+
+    for (int p = 0; p < P; ++p) {
+        const int j0 = p * W + lane * K - padL;   // column of this lane's k = 0 (negative: pad)
+        int H[K], Gy[K];
+        uint32_t C[K];
+        uint32_t selS[K];   // !GENERAL: PRMT selector of the score byte;   GENERAL: 4-bit set of the column
+        uint32_t selI[K];   // !GENERAL: PRMT selector of the count increment; GENERAL: 0 normal, 1 column 0, 2 pad
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            H[k] = Hinit; Gy[k] = 0; C[k] = 0;
+            if (!GENERAL) {
+                if (j < 0)       { selS[k] = 0xddd5u; selI[k] = 0x5555u; }
+                else if (j == 0) { selS[k] = 0xccc4u; selI[k] = 0x5654u; }
+                else { const uint32_t c = fetch2(ys, j); selS[k] = 0x8880u + 0x1111u * c; selI[k] = 0x5650u | c; }
+            } else {
+                if (j < 0)       { selS[k] = 0; selI[k] = 2; }
+                else             { selS[k] = fetch4(ys, j); selI[k] = (j == 0) ? 1u : 0u; }
+            }
+        }
+        int hprev = Hinit;
+        uint32_t cprev = 0;
+        int Hout = Hinit, Gxout = 0;
+        uint32_t cout = 0;
+        int4 nxt = make_int4(Hinit, 0, 0, 0);
+        if (p > 0 && lane == 0) nxt = __ldcg(&bbuf[0]);
+        uint32_t xcur = 0, xprev = 0;
+        if (lane < n) xcur = GENERAL ? fetch4(xs, lane) : fetch2(xs, lane);
+
+        const int T = n + 31;
+        for (int t = 0; t < T; ++t) {
+            const int r = t & 31;
+            if (r == 0 && t > 0) {
+                xprev = xcur;
+                const int ii = t + lane;
+                xcur = 0;
+                if (ii < n) xcur = GENERAL ? fetch4(xs, ii) : fetch2(xs, ii);
+            }
+            const uint32_t xv = (lane <= r) ? xcur : xprev;
+            const uint32_t xi = __shfl_sync(FULL_MASK, xv, (r - lane) & 31);
+            int hin = __shfl_up_sync(FULL_MASK, Hout, 1);
+            int gin = __shfl_up_sync(FULL_MASK, Gxout, 1);
+            uint32_t cin = __shfl_up_sync(FULL_MASK, cout, 1);
+            if (lane == 0) {
+                hin = nxt.x; gin = nxt.y; cin = (uint32_t)nxt.z;
+                if (p > 0 && t + 1 < n) nxt = __ldcg(&bbuf[t + 1]);
+            }
+            const int i = t - lane;
+            if (i >= 0 && i < n) {
+                int Hd = hprev, Gl = gin;
+                uint32_t cd = cprev, cl = cin;
+                if (!GENERAL) {
+                    const uint32_t sh = xi * 8u;
+                    const bool z = (i == 0);
+                    const uint32_t Rlo = (z ? baseZ : baseN) ^ ((z ? dZ : dN) << sh);
+                    const uint32_t Rhi = (xi == y0) ? c0m : c0x;            // byte4: column-0 score, byte5: 0 (pad)
+                    const uint32_t Mlo = 0x01010101u ^ (1u << sh);           // mismatch flags per base code
+                    const uint32_t Mhi = 0x00010000u | (xi != y0 ? 1u : 0u); // byte4: col-0 flag, byte5: 0, byte6: 1
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int s = (int)prmt(Rlo, Rhi, selS[k]);
+                        const uint32_t inc = prmt(Mlo, Mhi, selI[k]);
+                        const int Gu = Gy[k];
+                        const uint32_t cu = C[k];
+                        const int h = __vimax3_s32(Hd, Gu, Gl) + s;
+                        const int o = Hd + sc.go;
+                        const int gy = __viaddmax_s32(Gu, sc.ge, o);
+                        const int gx = __viaddmax_s32(Gl, sc.ge, o);
+                        const bool pD = (h >= gy) && (h >= gx);
+                        const bool pU = (gy >= gx);
+                        const uint32_t cdi = cd + inc;
+                        const uint32_t c = pD ? cdi : (pU ? cu : cl);
+                        Hd = H[k]; cd = cu;
+                        H[k] = h; Gy[k] = gy; C[k] = c;
+                        Gl = gx; cl = c;
+                    }
+                } else {
+                    const bool xgap = (xi == 0);
+                    const int sM = xgap ? INT_MIN : sc.match;
+                    const int sX = xgap ? INT_MIN : sc.mismatch;
+                    const bool row0 = (i == 0);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const uint32_t ym = selS[k];
+                        const uint32_t fl = selI[k];
+                        const uint32_t both = xi & ym;
+                        int s = both ? sM : sX;
+                        if (ym == 0) s = INT_MIN;
+                        const int Gu = Gy[k];
+                        const uint32_t cu = C[k];
+                        int mx = Hd > Gu ? Hd : Gu;
+                        mx = mx > Gl ? mx : Gl;
+                        int h = wadd(mx, s);
+                        const int o = wadd(Hd, sc.go);
+                        const int uy = wadd(Gu, sc.ge), lx = wadd(Gl, sc.ge);
+                        int gy = o > uy ? o : uy;
+                        int gx = o > lx ? o : lx;
+                        if (row0 || fl != 0) { gy = 0; gx = 0; }
+                        if (fl == 2) h = 0;
+                        const bool pD = (h >= gy) && (h >= gx);
+                        const bool pU = (gy >= gx);
+                        uint32_t inc = 0;
+                        if (!xgap && ym != 0) inc = 0x10000u + (both == 0 ? 1u : 0u);
+                        uint32_t c = pD ? cd + inc : (pU ? cu : cl);
+                        if (fl == 2) c = 0;
+                        if (DIRS && fl != 2) dirs[(size_t)i * (size_t)m + (size_t)(j0 + k)] = pD ? 0 : (pU ? 1 : 2);
+                        Hd = H[k]; cd = cu;
+                        H[k] = h; Gy[k] = gy; C[k] = c;
+                        Gl = gx; cl = c;
+                    }
+                }
+                hprev = hin; cprev = cin;
+                Hout = H[K - 1]; Gxout = Gl; cout = cl;
+                if (lane == 31) {
+                    if (p < P - 1) {
+                        __stcg(&bbuf[i], make_int4(Hout, Gxout, (int)cout, 0));
+                    } else if (Hout > colBest) {   // last column, rows ascending, strict >  (src/seqpair.cpp:137-139)
+                        colBest = Hout; colI = i; colC = cout;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // last row of this pass: columns ascending, strict >  (src/seqpair.cpp:140-142)
+        int bv = INT_MIN, bj = INT_MAX;
+        uint32_t bc = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            if (j >= 0 && H[k] > bv) { bv = H[k]; bj = j; bc = C[k]; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int ov = __shfl_xor_sync(FULL_MASK, bv, d);
+            const int oj = __shfl_xor_sync(FULL_MASK, bj, d);
+            const uint32_t oc = __shfl_xor_sync(FULL_MASK, bc, d);
+            if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; bc = oc; }
+        }
+        if (bj != INT_MAX && bv > rowBest) { rowBest = bv; rowJ = bj; rowC = bc; }
+    }
+    colBest = __shfl_sync(FULL_MASK, colBest, 31);
+    colI = __shfl_sync(FULL_MASK, colI, 31);
+    colC = __shfl_sync(FULL_MASK, colC, 31);
+    if (lane == 0) {
+        pa_pair_result o;
+        if (rowBest > colBest) { o.score = rowBest; o.end_i = n - 1; o.end_j = rowJ; o.dist = rowC & 0xffffu; o.len = rowC >> 16; }
+        else                   { o.score = colBest; o.end_i = colI;  o.end_j = m - 1; o.dist = colC & 0xffffu; o.len = colC >> 16; }
+        *res = o;
+    }
+}
+
+// Coalesced 128-bit staging of one packed sequence into this warp's shared
+// buffer; returns the pointer to read codes from (global if it does not fit).
+__device__ __forceinline__ const uint32_t *stage_seq(const uint32_t *g, uint32_t n_words, uint32_t *sm, int lane) {
+    if (n_words > (uint32_t)STAGE_WORDS) return g;
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+    uint4 *s4 = reinterpret_cast<uint4 *>(sm);
+    const uint32_t n4 = (n_words + 3) >> 2;
+    for (uint32_t w = lane; w < n4; w += 32) s4[w] = __ldg(&g4[w]);
+    return sm;
+}
+
+// Persistent warps pull pair indices from a global counter.
+//   !GENERAL: pairs with a non-A/C/G/T sequence are appended to `deferred`
+//             and handled by the GENERAL instantiation afterwards.
+template <int K, bool GENERAL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, const uint64_t count,
+                  unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
+                  pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
+    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1ull);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= count) break;
+        const uint64_t e = src.idx ? (uint64_t)src.idx[w] : (uint64_t)w;
+        uint32_t a, b;
+        if (src.ia) { a = src.ia[e]; b = src.ib[e]; }
+        else tri_pair(src.first + e, S.n_seq, a, b);
+        const int n = (int)S.len[a], m = (int)S.len[b];
+        if (n == 0 || m == 0) {   // the reference reads out of bounds here (src/seqpair.cpp:141); defined as "nothing compared"
+            if (lane == 0) { pa_pair_result o; o.score = INT_MIN; o.dist = 0; o.len = 0; o.end_i = n - 1; o.end_j = m - 1; out[e] = o; }
+            continue;
+        }
+        if (!GENERAL) {
+            if (!(S.pure[a] && S.pure[b])) {
+                if (lane == 0) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)e;
+                continue;
+            }
+        }
+        __syncwarp();
+        const uint32_t *xs, *ys;
+        if (GENERAL) {
+            xs = stage_seq(S.p4 + S.off4[a], (uint32_t)(n + 7) >> 3, stage[wib][0], lane);
+            ys = stage_seq(S.p4 + S.off4[b], (uint32_t)(m + 7) >> 3, stage[wib][1], lane);
+        } else {
+            xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
+            ys = stage_seq(S.p2 + S.off2[b], (uint32_t)(m + 15) >> 4, stage[wib][1], lane);
+        }
+        __syncwarp();
+        align_warp<K, GENERAL>(xs, n, ys, m, sc, bbuf, &out[e], lane);
+    }
+}
+
+// pairalign -A: position-wise comparison over min(n,m) columns of the raw
+// encoded sequences (src/pairalign.cpp:681, src/seqpair.cpp:238-274).  One warp
+// per pair, lanes stride over 8-base words.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_aligned_stats_kernel(const SeqStore S, const PairSource src, const uint64_t count,
+                        unsigned long long *work_counter, pa_pair_result *out) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1ull);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= count) break;
+        uint32_t a, b;
+        if (src.ia) { a = src.ia[w]; b = src.ib[w]; }
+        else tri_pair(src.first + w, S.n_seq, a, b);
+        const int n = (int)S.len[a], m = (int)S.len[b];
+        const int L = n < m ? n : m;
+        const uint32_t *xw = S.p4 + S.off4[a], *yw = S.p4 + S.off4[b];
+        uint32_t d = 0, l = 0;
+        for (int wd = lane; wd * 8 < L; wd += 32) {
+            uint32_t x = __ldg(&xw[wd]), y = __ldg(&yw[wd]);
+            const int rem = L - wd * 8;
+            if (rem < 8) { const uint32_t keep = (1u << (rem * 4)) - 1u; x &= keep; y &= keep; }
+            // per-nibble "non-zero" flags in bit 0 of each nibble
+            uint32_t nx = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+            uint32_t ny = (y | (y >> 1) | (y >> 2) | (y >> 3)) & 0x11111111u;
+            const uint32_t xy = x & y;
+            uint32_t nb = (xy | (xy >> 1) | (xy >> 2) | (xy >> 3)) & 0x11111111u;
+            const uint32_t cmp = nx & ny;
+            l += __popc(cmp);
+            d += __popc(cmp & ~nb);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            d += __shfl_xor_sync(FULL_MASK, d, s);
+            l += __shfl_xor_sync(FULL_MASK, l, s);
+        }
+        if (lane == 0) { pa_pair_result o; o.score = 0; o.dist = d; o.len = l; o.end_i = n - 1; o.end_j = m - 1; out[w] = o; }
+    }
+}
+
+// pairalign -a: one pair, moves kept (one byte per cell), then the reference's
+// walk back from the end cell (src/seqpair.cpp:146-178).  rx/ry receive the
+// aligned 4-bit sets in REVERSE order (the reference reverses at :183-188; the
+// host does that), *alen their count.  One warp.
+template <int K>
+__global__ void __launch_bounds__(32)
+pa_traceback_kernel(const SeqStore S, const Scoring sc, const uint32_t a, const uint32_t b, int4 *bbuf,
+                    uint8_t *dirs, pa_pair_result *res, uint8_t *rx, uint8_t *ry, uint32_t *alen) {
+    const int lane = threadIdx.x & 31;
+    const int n = (int)S.len[a], m = (int)S.len[b];
+    const uint32_t *xs = S.p4 + S.off4[a], *ys = S.p4 + S.off4[b];
+    align_warp<K, true, true>(xs, n, ys, m, sc, bbuf, res, lane, dirs);
+    __threadfence_block();
+    __syncwarp();
+    if (lane != 0) return;
+    int i = res->end_i, j = res->end_j;
+    uint32_t k = 0;
+    if (i < n - 1) {
+        for (int pos = n - 1; pos > i; --pos) { rx[k] = (uint8_t)fetch4(xs, pos); ry[k] = 0; ++k; }
+    } else if (j < m - 1) {
+        for (int pos = m - 1; pos > j; --pos) { rx[k] = 0; ry[k] = (uint8_t)fetch4(ys, pos); ++k; }
+    }
+    while (i >= 0 || j >= 0) {
+        uint8_t d = 3;
+        if (i >= 0 && j >= 0) d = dirs[(size_t)i * (size_t)m + (size_t)j];
+        if (d == 0) { rx[k] = (uint8_t)fetch4(xs, i); ry[k] = (uint8_t)fetch4(ys, j); --i; --j; }
+        else if (j < 0 || (i >= 0 && d == 1)) { rx[k] = (uint8_t)fetch4(xs, i); ry[k] = 0; --i; }
+        else { rx[k] = 0; ry[k] = (uint8_t)fetch4(ys, j); --j; }
+        ++k;
+    }
+    *alen = k;
+}
+
+}  // namespace pa

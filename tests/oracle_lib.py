@@ -1,0 +1,144 @@
+"""ctypes binding of oracle/liboracle.so and oracle/_ref/libref_seqpair.so.
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's CPU baseline
+may use this module.  Nothing here reads /root/reference at run time; the oracle is
+built by `make -C oracle` (phylommand_b200.build.build_oracle).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+REF_SO = ROOT / "oracle" / "_ref" / "libref_seqpair.so"
+REF_CLI = ROOT / "oracle" / "_ref" / "pairalign"
+REF_CLI_PTHREAD = ROOT / "oracle" / "_ref" / "pairalign_pthread"
+
+RESULT_DTYPE = np.dtype([("score", "<i4"), ("dist", "<u4"), ("len", "<u4"), ("end_i", "<i4"), ("end_j", "<i4")])
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.pa_oracle_char_mask.restype = C.c_int
+        lib.pa_oracle_char_mask.argtypes = [C.c_ubyte]
+        lib.pa_oracle_encode.restype = C.c_size_t
+        lib.pa_oracle_encode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        lib.pa_oracle_mask_char.restype = C.c_char
+        lib.pa_oracle_mask_char.argtypes = [C.c_uint8]
+        for name in ("pa_oracle_align_full",):
+            f = getattr(lib, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        lib.pa_oracle_align_forward.restype = C.c_int
+        lib.pa_oracle_align_forward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_void_p]
+        lib.pa_oracle_aligned_stats.restype = None
+        lib.pa_oracle_aligned_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        for name in ("pa_oracle_similarity", "pa_oracle_pdist", "pa_oracle_jc", "pa_oracle_diff"):
+            f = getattr(lib, name)
+            f.restype = C.c_double
+            f.argtypes = [C.c_uint32, C.c_uint32]
+        lib.pa_oracle_all_pairs.restype = C.c_int
+        lib.pa_oracle_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+
+    def encode(self, text) -> np.ndarray:
+        if isinstance(text, str):
+            text = text.encode("latin-1")
+        out = np.empty(max(len(text), 1), dtype=np.uint8)
+        n = self.lib.pa_oracle_encode(text, len(text), out.ctypes.data, None)
+        return out[:n].copy()
+
+    def decode(self, masks) -> str:
+        return b"".join(self.lib.pa_oracle_mask_char(int(m)) for m in masks).decode("ascii")
+
+    def align_full(self, x, y, match=7, mismatch=-5, go=-15, ge=-1):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        ax = np.empty(len(x) + len(y) + 1, dtype=np.uint8)
+        ay = np.empty(len(x) + len(y) + 1, dtype=np.uint8)
+        alen = C.c_int32(0)
+        rc = self.lib.pa_oracle_align_full(x.ctypes.data, len(x), y.ctypes.data, len(y), match, mismatch, go, ge,
+                                           res.ctypes.data, ax.ctypes.data, ay.ctypes.data, C.byref(alen))
+        assert rc == 0
+        return res[0], ax[:alen.value].copy(), ay[:alen.value].copy()
+
+    def align_forward(self, x, y, match=7, mismatch=-5, go=-15, ge=-1):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        rc = self.lib.pa_oracle_align_forward(x.ctypes.data, len(x), y.ctypes.data, len(y), match, mismatch, go, ge,
+                                              res.ctypes.data)
+        assert rc == 0
+        return res[0]
+
+    def aligned_stats(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        self.lib.pa_oracle_aligned_stats(x.ctypes.data, len(x), y.ctypes.data, len(y), res.ctypes.data)
+        return res[0]
+
+    def all_pairs(self, masks, offsets, first=0, last=None, threads=1, match=7, mismatch=-5, go=-15, ge=-1):
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if last is None:
+            last = n * (n - 1) // 2
+        out = np.zeros(last - first, dtype=RESULT_DTYPE)
+        rc = self.lib.pa_oracle_all_pairs(masks.ctypes.data, offsets.ctypes.data, n, match, mismatch, go, ge,
+                                          first, last, threads, out.ctypes.data)
+        assert rc == 0
+        return out
+
+    def similarity(self, d, l): return self.lib.pa_oracle_similarity(d, l)
+    def pdist(self, d, l): return self.lib.pa_oracle_pdist(d, l)
+    def jc(self, d, l): return self.lib.pa_oracle_jc(d, l)
+    def diff(self, d, l): return self.lib.pa_oracle_diff(d, l)
+
+
+class RefSeqpair:
+    """The UNMODIFIED reference seqpair class (oracle/_ref/libref_seqpair.so)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_seqpair_run.restype = C.c_int
+        lib.ref_seqpair_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_int]
+
+    def run(self, x: str, y: str, aligned: bool = False):
+        """x, y: raw text as pairalign passes it (first character is dropped by the reference)."""
+        cap = len(x) + len(y) + 8
+        ax = C.create_string_buffer(cap)
+        ay = C.create_string_buffer(cap)
+        score, ham = C.c_int(), C.c_int()
+        sim, jc = C.c_double(), C.c_double()
+        rc = self.lib.ref_seqpair_run(x.encode("latin-1"), y.encode("latin-1"), int(aligned), C.byref(score), C.byref(ham),
+                                      C.byref(sim), C.byref(jc), ax, ay, cap)
+        assert rc == 0
+        return dict(score=score.value, hamming=ham.value, sim=sim.value, jc=jc.value,
+                    x=ax.value.decode("ascii"), y=ay.value.decode("ascii"))
+
+
+def ensure_built() -> None:
+    if not ORACLE_SO.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "all"], check=True)
+
+
+def load() -> Oracle:
+    ensure_built()
+    return Oracle(C.CDLL(str(ORACLE_SO)))
+
+
+def load_ref():
+    """None when the compiled reference is not available (it is built in the authoring container)."""
+    if not REF_SO.exists():
+        return None
+    return RefSeqpair(C.CDLL(str(REF_SO)))

@@ -1,0 +1,212 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle.  Bit-exact for every
+integer output; floating-point figures are derived on the host from the integers with the
+reference's expressions, so they are compared bit-for-bit too (tolerance 0, which is inside
+the 1e-12 relative bound BASELINE.json states for JC distances)."""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from phylommand_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "seqpair_vectors.json").read_text())
+
+
+def _same(got, want):
+    bad = [k for k in range(len(want)) if tuple(got[k]) != tuple(want[k])]
+    assert not bad, f"{len(bad)} of {len(want)} pairs differ; first {bad[0]}: got {got[bad[0]]}, want {want[bad[0]]}"
+
+
+def _oracle_all(oracle, enc, threads=8, **kw):
+    masks, offsets = np.concatenate(enc), np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.uint64)
+    return oracle.all_pairs(masks, offsets, threads=threads, **kw)
+
+
+def test_golden_vectors_on_gpu(gpu, oracle):
+    """Every reference golden vector (unaligned and -A), one upload, explicit pair list."""
+    seqs, ia, ib, cases = [], [], [], []
+    for c in GOLDEN["cases"]:
+        x, y = gpu.encode(c["x"]), gpu.encode(c["y"])
+        if len(x) == 0 or len(y) == 0:
+            continue
+        ia.append(len(seqs)); seqs.append(x)
+        ib.append(len(seqs)); seqs.append(y)
+        cases.append(c)
+    gpu.upload(seqs)
+    ia, ib = np.array(ia), np.array(ib)
+    dp = gpu.align_pairs(ia, ib)
+    al = gpu.align_pairs(ia, ib, aligned=1)
+    for k, c in enumerate(cases):
+        r = al[k] if c["aligned"] else dp[k]
+        if not c["aligned"]:
+            assert int(r["score"]) == c["score"], c["tag"]
+        assert int(r["dist"]) == c["hamming"], c["tag"]
+        assert gpu.similarity(int(r["dist"]), int(r["len"])).hex() == c["sim"], c["tag"]
+        jc, want = gpu.jc_distance(int(r["dist"]), int(r["len"])), float.fromhex(c["jc"])
+        assert (math.isnan(jc) and math.isnan(want)) or jc.hex() == c["jc"], c["tag"]
+
+
+def test_golden_alignments_on_gpu(gpu):
+    """pairalign -a: aligned strings equal the reference's get_x()/get_y()."""
+    n = 0
+    for c in GOLDEN["cases"]:
+        if c["aligned"]:
+            continue
+        x, y = gpu.encode(c["x"]), gpu.encode(c["y"])
+        if len(x) == 0 or len(y) == 0 or len(x) * len(y) > 400 * 400:
+            continue
+        gpu.upload([x, y])
+        ax, ay, res = gpu.align_pair_traceback(0, 1, len(x) + len(y))
+        assert gpu.decode(ax) == c["ax"] and gpu.decode(ay) == c["ay"], c["tag"]
+        assert int(res["score"]) == c["score"]
+        n += 1
+    assert n > 100
+
+
+@pytest.mark.parametrize("lo,hi,n,seed", [(1, 40, 60, 1), (30, 200, 40, 2), (480, 560, 14, 3), (1000, 1100, 8, 4)])
+def test_all_pairs_pure_acgt(gpu, oracle, lo, hi, n, seed):
+    """2-bit register-wavefront kernel: ragged lengths, 1 to 3 passes of 512 columns."""
+    _, seqs = synth.make_random(n, seed, lo, hi)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    assert gpu.timing()["dp_general_ms"] == 0.0
+    _same(got, _oracle_all(oracle, enc))
+
+
+@pytest.mark.parametrize("iupac,gaps,lo,hi,n,seed", [(0.05, 0.0, 1, 60, 40, 5), (0.03, 0.0, 200, 300, 16, 6),
+                                                      (0.02, 0.15, 1, 80, 40, 7), (0.0, 0.2, 250, 330, 12, 8)])
+def test_all_pairs_iupac_and_gaps(gpu, oracle, iupac, gaps, lo, hi, n, seed):
+    """General kernel: IUPAC sets, and '-' in unaligned input (INT_MIN cost, 32-bit wrap-around)."""
+    _, seqs = synth.make_random(n, seed, lo, hi, iupac=iupac, gaps=gaps)
+    enc = [gpu.encode("N" + synth.to_text(s)) for s in seqs]
+    enc = [e if len(e) else np.array([1], dtype=np.uint8) for e in enc]
+    gpu.upload(enc)
+    _same(gpu.align_all_pairs(), _oracle_all(oracle, enc))
+
+
+def test_mixed_pure_and_ambiguous(gpu, oracle):
+    """Pure pairs run on the 2-bit kernel, the rest are deferred to the general kernel in the same call."""
+    _, a = synth.make_random(12, 11, 40, 700)
+    _, b = synth.make_random(12, 12, 40, 700, iupac=0.03)
+    enc = [gpu.encode("N" + synth.to_text(s)) for pair in zip(a, b) for s in pair]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_fast_ms"] > 0 and t["dp_general_ms"] > 0
+    _same(got, _oracle_all(oracle, enc))
+
+
+def test_other_scoring_parameters(gpu, oracle):
+    _, seqs = synth.make_random(14, 13, 20, 300, iupac=0.01)
+    enc = [gpu.encode("N" + synth.to_text(s)) for s in seqs]
+    gpu.upload(enc)
+    for match, mismatch, go, ge in ((7, -5, -15, -1), (5, -4, -10, -2), (1, -1, -2, 0), (10, -300, -20, -3), (2, -3, 4, 1)):
+        got = gpu.align_all_pairs(match=match, mismatch=mismatch, gap_open=go, gap_ext=ge)
+        _same(got, _oracle_all(oracle, enc, match=match, mismatch=mismatch, go=go, ge=ge))
+
+
+def test_sub_ranges_and_pair_lists(gpu, oracle):
+    _, seqs = synth.make_random(25, 21, 10, 120)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    want = _oracle_all(oracle, enc)
+    total = gpu.num_pairs()
+    assert total == 300
+    _same(gpu.align_all_pairs(17, 101), want[17:118])
+    _same(gpu.align_all_pairs(total - 1, 1), want[total - 1:])
+    assert len(gpu.align_all_pairs(5, 0)) == 0
+    idx = np.random.default_rng(0).permutation(total)[:77]
+    ab = np.array([gpu.pair_from_index(int(k)) for k in idx])
+    _same(gpu.align_pairs(ab[:, 0], ab[:, 1]), want[idx])
+    # both orders of the same pair are separate problems (end-cell tie rules are not symmetric)
+    rev = gpu.align_pairs(ab[:, 1], ab[:, 0])
+    for k in range(len(idx)):
+        assert tuple(rev[k]) == tuple(oracle.align_forward(enc[ab[k, 1]], enc[ab[k, 0]]))
+    with pytest.raises(gpu.PairalignError):
+        gpu.align_all_pairs(total, 1)
+    with pytest.raises(gpu.PairalignError):
+        gpu.align_pairs([0], [25])
+
+
+def test_aligned_mode(gpu, oracle):
+    """pairalign -A: position-wise over min(n,m) columns, gaps and IUPAC included."""
+    _, seqs = synth.make_random(20, 31, 1, 300, iupac=0.05, gaps=0.2)
+    enc = [gpu.encode("N" + synth.to_text(s)) for s in seqs]
+    enc = [e if len(e) else np.array([0], dtype=np.uint8) for e in enc]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs(aligned=1)
+    k = 0
+    for a in range(20):
+        for b in range(a + 1, 20):
+            assert tuple(got[k]) == tuple(oracle.aligned_stats(enc[a], enc[b])), (a, b)
+            k += 1
+
+
+def test_traceback_matches_oracle(gpu, oracle):
+    _, seqs = synth.make_random(10, 41, 5, 330, iupac=0.02, gaps=0.03)
+    enc = [gpu.encode("N" + synth.to_text(s)) for s in seqs]
+    gpu.upload(enc)
+    for a in range(10):
+        for b in (a + 1, (a + 5) % 10):
+            if a == b or b >= 10:
+                continue
+            ax, ay, res = gpu.align_pair_traceback(a, b, len(enc[a]) + len(enc[b]))
+            r, wx, wy = oracle.align_full(enc[a], enc[b])
+            assert tuple(res) == tuple(r)
+            assert ax.tolist() == wx.tolist() and ay.tolist() == wy.tolist()
+
+
+def test_partition_is_balanced_and_exact(gpu):
+    names, seqs, _ = synth.make_its_like(300, 1004)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    total = gpu.num_pairs()
+    lens = np.array([len(e) for e in enc], dtype=np.int64)
+    cells = int(((lens.sum() ** 2) - (lens ** 2).sum()) // 2)
+    assert gpu.count_cells(0, total) == cells
+    for parts in (1, 2, 4, 8):
+        b = gpu.partition_pairs(0, total, parts)
+        assert b[0] == 0 and b[-1] == total and np.all(np.diff(b.astype(np.int64)) >= 0)
+        shares = [gpu.count_cells(int(b[p]), int(b[p + 1] - b[p])) for p in range(parts)]
+        assert sum(shares) == cells
+        assert max(shares) - min(shares) <= 2 * int(lens.max()) ** 2
+
+
+def test_size_independent_properties_at_scale(gpu, oracle):
+    """Config-2-sized sequences (1.5 kb): self-consistency on the full set, oracle on a sample."""
+    names, seqs = synth.make_16s_like(96, 1002)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc + [enc[0]])          # a duplicate of sequence 0 at the end
+    got = gpu.align_all_pairs()
+    n = len(enc) + 1
+    lens = np.array([len(e) for e in enc] + [len(enc[0])])
+    k = 0
+    for a in range(n):
+        for b in range(a + 1, n):
+            r = got[k]
+            assert r["dist"] <= r["len"] <= min(lens[a], lens[b])
+            assert r["score"] <= 7 * min(lens[a], lens[b])
+            assert (r["end_i"] == lens[a] - 1) or (r["end_j"] == lens[b] - 1)
+            if a == 0 and b == n - 1:      # identical sequences: full-length diagonal
+                assert (r["score"], r["dist"], r["len"]) == (7 * lens[0], 0, lens[0])
+            k += 1
+    sample = np.random.default_rng(1).choice(len(got), size=120, replace=False)
+    for q in sample:
+        a, b = gpu.pair_from_index(int(q))
+        ea = enc[a] if a < len(enc) else enc[0]
+        eb = enc[b] if b < len(enc) else enc[0]
+        assert tuple(got[q]) == tuple(oracle.align_forward(ea, eb)), (a, b)
+
+
+def test_long_pair_many_passes(gpu, oracle):
+    """A 9 kb x 7 kb pair: 14-18 passes, sequences read from global memory instead of the staging buffer."""
+    _, seqs = synth.make_long(2, 1005, length=8000, spread=0.12)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    assert tuple(got[0]) == tuple(oracle.align_forward(enc[0], enc[1]))
