@@ -220,6 +220,8 @@ int pa_oracle_align_forward(const uint8_t *x, int32_t n, const uint8_t *y, int32
     }
     for (int32_t j = 0; j < m; ++j)
         if (A[j] > best) { best = A[j]; bi = n - 1; bj = j; bd = cd[j]; bl = cl[j]; }
+    /* every candidate equals INT_MIN: the reference keeps its initial i=n-1, j=m-1 (:132-133) */
+    if (best == INT_MIN) { bd = cd[m - 1]; bl = cl[m - 1]; }
     res->score = best; res->end_i = bi; res->end_j = bj; res->dist = bd; res->len = bl;
     free(A); free(Gy); free(cd); free(cl);
     return 0;

@@ -212,7 +212,9 @@ def timing() -> dict:
 
 PEAK_CLASSES = {0: "IADD3", 1: "VIMNMX3", 2: "VIADDMNMX", 3: "IMAD", 4: "PRMT", 5: "ISETP+SEL", 6: "IADD3+IMAD mix",
                 7: "VIMNMX3.S16x2", 8: "VIADDMNMX.S16x2", 9: "VIADD.16x2", 10: "LOP3", 11: "SHFL", 12: "VIMNMX",
-                13: "VIADDMNMX+IMAD mix"}
+                13: "VIADDMNMX+IMAD mix",
+                18: "VIADDMNMX+IMAD imm mix", 19: "VIADDMNMX x3 + IMAD imm", 20: "PRMT+LOP3",
+                21: "VIADDMNMX.S16x2+IMAD imm mix"}
 
 
 def int32_peak(which: int) -> tuple[float, float]:

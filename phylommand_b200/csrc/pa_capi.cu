@@ -65,6 +65,7 @@ struct Device {
     size_t d_pairs_cap = 0;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_done[2] = {};
+    bool chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
     // timing accumulators of the last call
     double fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
     uint32_t launches = 0;
@@ -191,7 +192,9 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     PairSource src{first, d_ia, d_ib, nullptr};
     CU(cudaMemsetAsync(d.counters, 0, 2 * sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.n_deferred, 0, sizeof(unsigned int), d.stream));
+    d.chunk_fast = d.chunk_gen = false;
     if (p.aligned) {
+        d.chunk_fast = true;
         CU(cudaEventRecord(d.ev[0], d.stream));
         pa_aligned_stats_kernel<<<d.grid_stats, WARPS_PER_CTA * 32, 0, d.stream>>>(S, src, count, d.counters, d_out);
         CU(cudaGetLastError());
@@ -210,6 +213,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             S, sc, src, count, d.counters, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
+        d.chunk_fast = true;
     }
     CU(cudaEventRecord(d.ev[1], d.stream));
     CU(cudaEventRecord(d.ev[2], d.stream));
@@ -218,6 +222,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             S, sc, src, count, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
+        d.chunk_gen = true;
     } else if (!c.all_pure) {
         PairSource s2 = src;
         s2.idx = d.deferred;
@@ -225,6 +230,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             S, sc, s2, d.n_deferred, d.counters + 1, d.bbuf, d.bbuf_rows, d_out);
         CU(cudaGetLastError());
         d.launches += 1;
+        d.chunk_gen = true;
     }
     CU(cudaEventRecord(d.ev[3], d.stream));
     return PA_OK;
@@ -233,9 +239,9 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
 int collect_chunk_times(Device &d) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
-    d.fast_ms += ms;
+    if (d.chunk_fast) d.fast_ms += ms;
     CU(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]));
-    d.gen_ms += ms;
+    if (d.chunk_gen) d.gen_ms += ms;
     return PA_OK;
 }
 

@@ -118,7 +118,7 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
 
     int rowBest = INT_MIN, rowJ = 0;
     uint32_t rowC = 0;
-    int colBest = INT_MIN, colI = 0;
+    int colBest = INT_MIN, colI = n - 1;
     uint32_t colC = 0;
 
     // fast-path constants
@@ -247,8 +247,11 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                 if (lane == 31) {
                     if (p < P - 1) {
                         __stcg(&bbuf[i], make_int4(Hout, Gxout, (int)cout, 0));
-                    } else if (Hout > colBest) {   // last column, rows ascending, strict >  (src/seqpair.cpp:137-139)
-                        colBest = Hout; colI = i; colC = cout;
+                    } else {
+                        // last column, rows ascending, strict >  (src/seqpair.cpp:137-139)
+                        if (Hout > colBest) { colBest = Hout; colI = i; colC = cout; }
+                        // nothing above INT_MIN anywhere: the reference stays on its initial (n-1, m-1)  (:132-133)
+                        if (i == n - 1 && colBest == INT_MIN) colC = cout;
                     }
                 }
             }
