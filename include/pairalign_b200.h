@@ -90,6 +90,7 @@ typedef struct {
 int pa_init(const int *devices, int n_dev);
 void pa_shutdown(void);
 int pa_device_count(void);          /* devices in the context (0 if none)      */
+int pa_visible_devices(void);       /* CUDA devices this process can see (0 if none) */
 int pa_api_version(void);
 const char *pa_last_error(void);
 

@@ -37,6 +37,7 @@ SYMBOLS = {
     "pa_init": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "pa_shutdown": (None, []),
     "pa_device_count": (C.c_int, []),
+    "pa_visible_devices": (C.c_int, []),
     "pa_api_version": (C.c_int, []),
     "pa_last_error": (C.c_char_p, []),
     "pa_char_to_mask": (C.c_int, [C.c_ubyte]),

@@ -392,6 +392,12 @@ void pa_shutdown(void) {
 
 int pa_device_count(void) { return g_ctx ? (int)g_ctx->dev.size() : 0; }
 
+int pa_visible_devices(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
 // ---- front end --------------------------------------------------------------
 int pa_char_to_mask(unsigned char ch) {
     // bit0 A, bit1 G, bit2 C, bit3 T; unions for the IUPAC codes; '-' empty; N and '.' everything

@@ -1,0 +1,677 @@
+// pairalign_main.cpp -- the pairalign command line on top of the B200 module.
+//
+// Same flags, same stdout (byte for byte) and the same files as the reference's
+// pairalign (src/pairalign.cpp), but the all-pairs loop is turned inside out:
+// the reference pulls one pair at a time through seqdatabase and aligns it on
+// the spot (cluster(), src/pairalign.cpp:495-665 -> align_pair(), :675-861);
+// here every sequence is read and encoded once, the pairs are aligned in large
+// batches by the CUDA module (include/pairalign_b200.h) while a second thread
+// replays the finished batch -- matrix framing, per-pair text, the single-link
+// clustering state machine and the MAD histograms -- strictly in the
+// reference's pair order, because that order is observable.
+//
+// There is no CPU alignment path: without a CUDA device the program stops with
+// an error.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <algorithm>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cluster_store.h"
+#include "fasta_index.h"
+#include "mad_groups.h"
+#include "pairalign_b200.h"
+#include "seqpair_batch.h"
+
+namespace {
+
+using namespace pab;
+
+const char *kVersion = "1.1";   // src/constants.h:26
+const char *kYear = "2019";     // src/constants.h:27
+
+struct Options {
+    char output_mode = 'a';
+    bool matrix = false;
+    bool quiet = true;
+    bool output_names = false;
+    bool aligned = false;
+    std::string file_name;
+    std::string taxonomy_file;
+    std::string cut_off = "all,0.999";     // src/pairalign.cpp:126
+    int min_length = 100;
+    bool only_lead = false;
+    std::string format = "fasta";
+    int n_threads = 1;
+};
+
+// argv_parser::pars_sub_args (src/argv_parser.cpp:53-72): split on `sep`, backslash escapes
+std::vector<std::string> split_sub_args(const char *arg, char sep) {
+    std::vector<std::string> out(1);
+    bool escape = false;
+    for (const char *p = arg; *p; ++p) {
+        char c = *p;
+        if (c == '\\' && !escape) { escape = true; continue; }
+        if (escape) { if (c == 'n') c = '\n'; else if (c == 'r') c = '\r'; else if (c == 't') c = '\t'; }
+        if (c == sep && !escape) out.emplace_back();
+        else out.back() += c;
+        escape = false;
+    }
+    return out;
+}
+
+void print_help() {
+    // src/pairalign.cpp:312-403 (default build: no DATABASE; -T is accepted but batches replace threads)
+    std::cout << "Pairalign " << kVersion << " will perform pairwise alignment of DNA sequences given in fasta\n"
+              << "format through standard in.\n"
+              << "(c) Martin Ryberg " << kYear << ".\n\n"
+              << "Usage:\npairalign [arguments] < inputfile.fasta\npairalign [arguments] inputfile.fasta\n\n"
+              << "Arguments:\n"
+              << "--aligned / -A                  input file is already aligned.\n"
+              << "--alignments / -a               output aligned sequences pairwise.\n"
+              << "--difference / -i               output difference between the Jukes-Cantor (JC)\n"
+              << "                                distance and proportion different sites.\n"
+              << "--distances / -d                output proportion different sites, JC distance,\n"
+              << "                                and diference between the two.\n"
+              << "--format [fasta/pairfst]        set the format of the input to fasta or fasta\n"
+              << "                                with sequences pairwise (as output given the -a\n"
+              << "                                -n option). If sequences are aligned give the -A\n"
+              << "                                switch.\n"
+              << "--group / -g                    this option will cluster sequences that are\n"
+              << "                                similar and/or find the most inclusive taxa in a\n"
+              << "                                hierarchy that are alignable according to MAD\n"
+              << "                                (Smith et al. 2009, BMC evol. Biol. 9:37). It\n"
+              << "                                need the taxonomy given after a (the first) | in\n"
+              << "                                the sequence name or in a separate file. Each\n"
+              << "                                taxa in the hierarchy should be separated by a\n"
+              << "                                semicolon, with the highest rank first and then\n"
+              << "                                increasingly nested levels until the lowest\n"
+              << "                                known level for the sequence. The groups that\n"
+              << "                                can be aligned are put in a file with the ending\n"
+              << "                                .alignment_groups and printed to the screen\n"
+              << "                                preceded by #. Clusters are printed to the\n"
+              << "                                screen after a heading, preceded by ###. To get\n"
+              << "                                alignable groups give 'alignment_groups' as\n"
+              << "                                extra argument, to cluster give 'cluster', and\n"
+              << "                                to do both give 'both'. Cut off value for\n"
+              << "                                pairwise similarity can be given after colon (:)\n"
+              << "                                by cut-off= followed value, e.g. -g both:\n"
+              << "                                cut-off=0.97. A file with taxonomy can be given\n"
+              << "                                with taxonomy=. The taxonomy file should have\n"
+              << "                                the taxonomy (as above) first on each row\n"
+              << "                                followed by a |, and the sequence name with that\n"
+              << "                                taxonomy as a comma (,) and/or space ( )\n"
+              << "                                separated string. The same taxon can be repeated\n"
+              << "                                several times.\n"
+              << "--help / -h                     print this help.\n"
+              << "--jc_distance / -j              output Jukes-Cantor (JC) distance.\n"
+              << "--matrix / -m                   output in the form of a space separated\n"
+              << "                                left-upper triangular matrix.\n"
+              << "--names / -n                    output sequence names (if outputting alignments\n"
+              << "                                then in fasta format).\n"
+              << "--proportion_difference / -p    output proportion sites that are different.\n"
+              << "--similarity / -s               output similarity between sequences (1-proportion\n"
+              << "                                different).\n"
+              << "--verbose / -v                  get additional output.\n";
+    std::cout.flush();
+}
+
+// ---- buffered stdout with the reference's number formatting -------------------
+// `ostream << double` at default precision is printf("%g").
+class Out {
+public:
+    ~Out() { flush(); }
+    void put(char c) { buf_ += c; maybe_flush(); }
+    void put(const std::string &s) { buf_ += s; maybe_flush(); }
+    void put(const char *s) { buf_ += s; maybe_flush(); }
+    void num(double v) {
+        char tmp[40];
+        const int n = std::snprintf(tmp, sizeof tmp, "%g", v);
+        buf_.append(tmp, (size_t)n);
+        maybe_flush();
+    }
+    void flush() {
+        if (!buf_.empty()) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); }
+        std::fflush(stdout);
+    }
+private:
+    void maybe_flush() { if (buf_.size() > (1u << 20)) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); } }
+    std::string buf_;
+};
+
+// ---- what one replayed pair needs ------------------------------------------------
+struct PairView {
+    const std::string *accno1, *accno2;
+    long seq1, seq2;                 // indices into the SeqpairBatch (seq2 < 0: the reference's empty second sequence)
+    long cid1, cid2;                 // indices into the cluster store (ascending accession order)
+    bool new_row;                    // seqdatabase::at_new_first() (src/seqdatabase.h:135-138)
+};
+
+// Everything align_pair() does after align() (src/pairalign.cpp:690-856).
+class Replayer {
+public:
+    Replayer(const Options &o, float cut_off, SeqpairBatch &batch, Out &out)
+        : opt_(o), cut_off_(cut_off), batch_(batch), out_(out) {}
+
+    std::function<std::string(const PairView &, int)> taxon_of;   // get_taxon_string of side 1 / 2 (src/seqdatabase.h:106-114)
+    std::function<float(long)> comp_of;                           // get_comp_value(accession or lead) (src/seqdatabase.h:97-105)
+    ClusterStore clusters;
+    MadGroups deviations;
+
+    void begin_row(const std::string &accno1) {      // src/pairalign.cpp:594-602
+        ++n_seq_;
+        if (n_seq_ > 1) out_.put('\n');
+        if (opt_.output_names) { out_.put(accno1); out_.put(' '); }
+        for (unsigned int i = 1; i < n_seq_; ++i) out_.put(' ');
+    }
+
+    void pair(const PairView &v, const PairStats &st, const pa_params &params) {
+        if (opt_.matrix && v.new_row) begin_row(*v.accno1);
+        if (batch_.any_unknown()) {           // the reference re-encodes (and re-warns) per pair
+            batch_.warn_unknown((size_t)v.seq1);
+            if (v.seq2 >= 0) batch_.warn_unknown((size_t)v.seq2);
+        }
+        const char mode = opt_.output_mode;
+        if (mode == 'A' || mode == 'B') group(v, st);
+        else if (mode == 'a') {
+            std::string x, y;
+            if (v.seq2 >= 0) batch_.alignment(params, (uint32_t)v.seq1, (uint32_t)v.seq2, x, y);
+            else { x = batch_.text((size_t)v.seq1); y.assign(x.size(), '-'); }
+            if (opt_.output_names) { out_.put('>'); out_.put(*v.accno1); out_.put('\n'); }
+            out_.put(x); out_.put('\n');
+            if (opt_.output_names) { out_.put('>'); out_.put(*v.accno2); out_.put('\n'); }
+            out_.put(y); out_.put('\n');
+        } else if (mode == 'd') {
+            if (!opt_.matrix) {
+                names(v);
+                out_.put("Proportion sites that are different (and similarity): ");
+                out_.num(st.proportion_different()); out_.put(" ("); out_.num(st.similarity());
+                out_.put("), Jukes-Cantor distance: "); out_.num(st.jc_distance());
+                out_.put(", difference between the two: "); out_.num(st.jc_minus_p()); out_.put(".\n");
+            } else {
+                out_.num(st.proportion_different()); out_.put('/'); out_.num(st.similarity()); out_.put('/');
+                out_.num(st.jc_distance()); out_.put('/'); out_.num(st.jc_minus_p()); out_.put('.');
+            }
+        } else if (mode == 'c') scalar(v, st.jc_minus_p());
+        else if (mode == 'j') scalar(v, st.jc_distance());
+        else if (mode == 'p') scalar(v, st.proportion_different());
+        else if (mode == 's') scalar(v, st.similarity());
+        // mode 'C' (-g cluster) falls through every branch of the reference's align_pair: nothing happens
+        if (!opt_.quiet) std::cerr << '.';
+    }
+
+private:
+    void names(const PairView &v) {
+        if (opt_.output_names) { out_.put(*v.accno1); out_.put(" - "); out_.put(*v.accno2); out_.put(" | "); }
+    }
+    void scalar(const PairView &v, double value) {
+        if (!opt_.matrix) { names(v); out_.num(value); out_.put('\n'); }
+        else { out_.num(value); out_.put(' '); }
+    }
+
+    // src/pairalign.cpp:690-805
+    void group(const PairView &v, const PairStats &st) {
+        const long a1 = v.cid1, a2 = v.cid2;
+        const std::string tax1 = taxon_of(v, 1), tax2 = v.seq2 >= 0 ? taxon_of(v, 2) : std::string();
+        if (cut_off_ > 0.000000001 && v.seq2 >= 0) {
+            const long c1 = clusters.get_cluster(a1), c2 = clusters.get_cluster(a2);
+            const bool free1 = (c1 == ClusterStore::EMPTY || c1 == ClusterStore::LEAD);
+            const bool free2 = (c2 == ClusterStore::EMPTY || c2 == ClusterStore::LEAD);
+            if (st.similarity() > cut_off_) {
+                const float comp1 = comp_of(free1 ? a1 : c1);
+                const float comp2 = comp_of(free2 ? a2 : c2);
+                // the better (longer, fewer N) sequence or cluster absorbs the other
+                if (comp1 >= comp2) absorb(a1, c1, a2, c2, free2);
+                else absorb(a2, c2, a1, c1, free1);
+            } else {
+                if (c1 == ClusterStore::EMPTY) upd(a1, ClusterStore::LEAD, true);
+                if (c2 == ClusterStore::EMPTY) upd(a2, ClusterStore::LEAD, true);
+                if (!tax1.empty() && tax1 != "empty" && !tax2.empty() && tax2 != "empty" && free1 && free2)
+                    deviations.insert_value(tax1, tax2, (float)st.jc_minus_p());
+            }
+        } else {
+            deviations.insert_value(tax1, tax2, (float)st.jc_minus_p());
+        }
+    }
+    // winner w (cluster state cw) takes in loser l (cluster state cl); src/pairalign.cpp:717-775
+    void absorb(long w, long cw, long l, long cl, bool l_free) {
+        long target;
+        if (cw == ClusterStore::EMPTY) { upd(w, ClusterStore::LEAD, true); target = w; }
+        else if (cw == ClusterStore::LEAD) target = w;
+        else { if (cw == cl) return; target = cw; }        // already in the same cluster
+        upd(l, target, true);
+        if (l_free) upd(l, target, false);
+        else { upd(cl, target, true); upd(cl, target, false); }
+    }
+    void upd(long accno, long cluster, bool where_accno) {
+        if (!clusters.update(accno, cluster, where_accno))
+            std::cerr << "Warning!!! Accession number cluster name collision when updating clusters." << std::endl;
+    }
+
+    const Options &opt_;
+    const float cut_off_;
+    SeqpairBatch &batch_;
+    Out &out_;
+    unsigned int n_seq_ = 0;
+};
+
+// cut-off string "gene,value,gene,value" or a bare number (src/pairalign.cpp:456-479)
+float parse_cut_off(const std::string &cut_off, const std::string &table) {
+    float present = 0.0f;
+    const int length = (int)cut_off.length();
+    std::string gene;
+    int i = 0;
+    for (; i < length; ++i) {
+        if (cut_off[i] == ',') {
+            if (gene == table || gene == "all") {
+                std::string number;
+                ++i;
+                while (i < length && cut_off[i] != ',') { number += cut_off[i]; ++i; }
+                present = (float)atof(number.c_str());
+                gene.clear();
+                break;
+            }
+        } else gene += cut_off[i];
+    }
+    if (i > 0 && i >= length && !gene.empty() && (std::isdigit((unsigned char)gene[0]) || gene[0] == '.'))
+        present = (float)atof(gene.c_str());
+    return present;
+}
+
+// taxonomy file: "tax1; tax2|acc1,acc2 acc3" per row (src/pairalign.cpp:409-439)
+bool read_taxonomy(const std::string &path, std::map<std::string, std::string> &tax) {
+    std::ifstream f(path.c_str());
+    if (!f.good()) { std::cerr << "Was not able to open " << path << ". No taxonomy read." << std::endl; return false; }
+    std::string taxa, accno;
+    bool taxonomy = true;
+    while (f) {
+        const char c = (char)f.get();
+        if (c == '|' && taxonomy) taxonomy = false;
+        else if (!taxonomy && (c == ' ' || c == ',' || c == '\n' || c == '\r') && !accno.empty() && !taxa.empty()) {
+            tax[accno] = taxa;
+            accno.clear();
+            if (c == '\r' || c == '\n') { taxonomy = true; taxa.clear(); }
+        } else if (c == '\r' || c == '\n') { taxonomy = true; taxa.clear(); }
+        else if (taxonomy) taxa += c;
+        else accno += c;
+    }
+    if (tax.empty()) { std::cerr << "Was not able to pars taxonomy from " << path << "." << std::endl; return false; }
+    return true;
+}
+
+std::string lookup_taxonomy(const std::map<std::string, std::string> &tax, const std::string &accno) {
+    auto it = tax.find(accno);            // get_taxon_string_from_map (src/seqdatabase.h:304-311)
+    if (it != tax.end()) return it->second;
+    it = tax.find("default");
+    if (it != tax.end()) return it->second;
+    return std::string();
+}
+
+// Double-buffered batches: the CUDA module fills one buffer while the caller replays the other.
+template <class Produce, class Consume>
+void pipeline(uint64_t total, uint64_t chunk, Produce produce, Consume consume) {
+    if (total == 0) return;
+    std::vector<pa_pair_result> buf[2];
+    std::string error;
+    auto fill = [&](int slot, uint64_t first) {
+        const uint64_t n = std::min<uint64_t>(chunk, total - first);
+        buf[slot].resize((size_t)n);
+        try { produce(first, n, buf[slot].data()); } catch (const std::exception &e) { error = e.what(); }
+    };
+    int slot = 0;
+    fill(0, 0);
+    for (uint64_t first = 0; first < total; first += chunk) {
+        if (!error.empty()) throw std::runtime_error(error);
+        const uint64_t next = first + chunk;
+        std::thread worker;
+        if (next < total) worker = std::thread(fill, slot ^ 1, next);
+        consume(first, buf[slot]);
+        if (worker.joinable()) worker.join();
+        slot ^= 1;
+    }
+}
+
+constexpr uint64_t kChunkPairs = 1ull << 21;
+
+// ---- fasta input: all pairs of the file -------------------------------------------
+void run_fasta(const Options &opt, Out &out) {
+    FastaIndex index;
+    index.open(opt.file_name);
+    if (!opt.quiet) std::cerr << "Opened " << opt.format << " database." << std::endl;
+    std::map<std::string, std::string> taxonomy;
+    if (!opt.taxonomy_file.empty()) {
+        if (!opt.quiet) std::cerr << "Parsing taxonomy from " << opt.taxonomy_file << "." << std::endl;
+        if (read_taxonomy(opt.taxonomy_file, taxonomy) && !opt.quiet) std::cerr << "Added taxonomy." << std::endl;
+    }
+    const char mode = opt.output_mode;
+    std::ofstream groups_file;
+    if (mode == 'A' || mode == 'B') {
+        if (!opt.quiet) std::cerr << "No alignment_groups file/table present. Trying to create it." << std::endl;
+        const std::string name = opt.file_name.empty() ? "sequence.alignment_groups" : opt.file_name + ".alignment_groups";
+        groups_file.open(name.c_str());
+        if (!groups_file.is_open()) { std::cerr << "Failed to create alignment_groups." << std::endl; return; }
+    }
+    const std::string table = opt.file_name;     // the single pseudo-table (src/seqdatabase.h:254-258)
+    float cut_off = 0.0f;
+    if (mode == 'B' || mode == 'C') {
+        cut_off = parse_cut_off(opt.cut_off, table);
+        if (cut_off < 0.000000001) {
+            std::cerr << "Could not find appropriate cut off (" << cut_off << ") for " << table
+                      << ". Will only define alignment groups and not cluster." << std::endl;
+            return;
+        }
+        if (!opt.quiet) std::cerr << "Using the cut off: " << cut_off << "." << std::endl;
+    }
+    if (!opt.quiet) std::cerr << "Checking " << table << std::endl;
+    if (!opt.quiet) std::cerr << "Starting pairwise alignment." << std::endl;
+
+    const size_t N = index.size();
+    SeqpairBatch batch;
+    Replayer rp(opt, cut_off, batch, out);
+    if (N == 0) {
+        std::cerr << "Could not initiate sequence retrieval. No aligning done for " << table << "." << std::endl;
+    } else {
+        for (size_t s = 0; s < N; ++s) batch.add_sequence(index[s].text);
+        rp.clusters.reset(N);
+        rp.taxon_of = [&](const PairView &v, int side) {
+            const FastaRecord &r = index[(size_t)(side == 1 ? v.seq1 : v.seq2)];
+            return taxonomy.empty() ? r.taxon : lookup_taxonomy(taxonomy, r.accno);
+        };
+        rp.comp_of = [&](long s) { return index[(size_t)s].comp_value(); };
+        if (opt.matrix && mode == 'd')
+            out.put("Proportion different/Similarity/Jukes-Cantor distance/Difference between JC and similarity\n");
+        pa_params params{7, -5, -15, -1, opt.aligned ? 1 : 0};      // src/pairalign.cpp:682, src/seqpair.h:57-58
+        if (N == 1) {
+            // the reference still visits one pair whose second sequence is empty (src/seqdatabase.cpp:108);
+            // nothing can be compared: similarity 1, JC -0
+            static const std::string none;
+            PairView v{&index[0].accno, &none, 0, -1, 0, -1, true};
+            PairStats st{{0, 0, 0, (int)batch.length(0) - 1, -1}};
+            rp.pair(v, st, params);
+        } else {
+            const bool need_stats = (mode != 'a' && mode != 'C');
+            const uint64_t total = (uint64_t)N * (N - 1) / 2;
+            if (need_stats || mode == 'a') { init_devices(); batch.upload(); }
+            uint32_t a = 0, b = 0;       // pair cursor in reference order: (0,1),(0,2)..(1,2)..
+            auto consume = [&](uint64_t first, const std::vector<pa_pair_result> &recs) {
+                (void)first;
+                for (size_t k = 0; k < recs.size(); ++k) {
+                    if (b == 0) { a = 0; b = 1; }
+                    PairView v{&index[a].accno, &index[b].accno, (long)a, (long)b, (long)a, (long)b, b == a + 1};
+                    PairStats st{recs[k]};
+                    rp.pair(v, st, params);
+                    if (++b == N) { ++a; b = a + 1; }
+                }
+            };
+            auto produce = [&](uint64_t first, uint64_t n, pa_pair_result *dst) {
+                if (need_stats) batch.align_range(params, first, n, dst);
+                else std::memset(dst, 0, (size_t)n * sizeof(pa_pair_result));
+            };
+            pipeline(total, kChunkPairs, produce, consume);
+            // src/pairalign.cpp:629-630 -- printed with or without -n
+            if (opt.matrix) { out.put('\n'); out.put(index[N - 1].accno); out.put('\n'); }
+        }
+    }
+    if (!opt.quiet) std::cerr << std::endl;
+    if (mode == 'A' || mode == 'B') {
+        if (!opt.quiet)
+            std::cerr << "Finished aligning. Calculating mad to determine taxonomic level suitable for alignment." << std::endl;
+        const std::string levels = rp.deviations.get_levels();
+        out.put("# Alignment groups for "); out.put(table); out.put('\n');
+        out.put("#    Alignment groups: "); out.put(levels); out.put('\n');
+        if (!opt.quiet) std::cerr << "    Aprox. mad. entire group = " << rp.deviations.approx_mad() << std::endl;
+        if (groups_file.good()) groups_file << table << "\t" << levels << std::endl;
+    }
+    if (mode == 'B' || mode == 'C') {
+        out.flush();
+        std::cout << "### Clusters " << table << ", cut-off: " << cut_off << " ###" << std::endl;
+        rp.clusters.print(std::cout, [&](long s) -> const std::string & { return index[(size_t)s].accno; });
+        std::cout.flush();
+    }
+}
+
+// ---- pair-fasta input: consecutive record pairs (src/seqdatabase.cpp:34-67) -------
+struct PairRecord {
+    std::string accno1, accno2, seq1, seq2, tax1, tax2;
+    bool new_row;
+};
+
+void run_pairfasta(const Options &opt, Out &out) {
+    std::ifstream file;
+    std::istream *input = &std::cin;
+    if (!opt.file_name.empty()) { file.open(opt.file_name.c_str()); input = &file; }
+    if (!opt.quiet) std::cerr << "Opened pairfa database." << std::endl;
+    std::map<std::string, std::string> taxon_strings;
+    if (!opt.taxonomy_file.empty()) read_taxonomy(opt.taxonomy_file, taxon_strings);
+    else taxon_strings["default"] = "all";                     // src/pairalign.cpp:440-445
+    const char mode = opt.output_mode;
+    std::ofstream groups_file;
+    if (mode == 'A' || mode == 'B') {
+        const std::string name = opt.file_name.empty() ? "sequence.alignment_groups" : opt.file_name + ".alignment_groups";
+        groups_file.open(name.c_str());
+        if (!groups_file.is_open()) { std::cerr << "Failed to create alignment_groups." << std::endl; return; }
+    }
+    const std::string table = opt.file_name;
+    float cut_off = 0.0f;
+    if (mode == 'B' || mode == 'C') {
+        cut_off = parse_cut_off(opt.cut_off, table);
+        if (cut_off < 0.000000001) {
+            std::cerr << "Could not find appropriate cut off (" << cut_off << ") for " << table
+                      << ". Will only define alignment groups and not cluster." << std::endl;
+            return;
+        }
+    }
+    // read every pair with the reference's character state machine; taxon strings found in the
+    // headers are APPENDED to the map each time an accession is seen (src/seqdatabase.cpp:55-56)
+    std::vector<PairRecord> pairs;
+    std::string previous = "empty", last_accno2;
+    bool ok = opt.file_name.empty() || file.good();
+    while (ok) {
+        PairRecord r;
+        char read_mode = '0';
+        while (*input) {
+            const char c = (char)input->get();
+            if (c == '>') { if (read_mode == '0') read_mode = 'A'; else if (read_mode == 'S') read_mode = 'a'; }
+            else if (c == '|') { if (read_mode == 'A') read_mode = 'T'; else if (read_mode == 'a') read_mode = 't'; }
+            else if (c == '\n' || c == '\r') {
+                if (read_mode == 'A' || read_mode == 'T') read_mode = 'S';
+                else if (read_mode == 'a' || read_mode == 't') read_mode = 's';
+            }
+            else if (read_mode == 'A') r.accno1 += c;
+            else if (read_mode == 'a') r.accno2 += c;
+            else if (read_mode == 'T') taxon_strings[r.accno1] += c;
+            else if (read_mode == 't') taxon_strings[r.accno2] += c;
+            else if (read_mode == 'S') r.seq1 += c;
+            else if (read_mode == 's') r.seq2 += c;
+            if (read_mode == 's' && (input->peek() == '>' || input->peek() == EOF)) break;
+        }
+        r.new_row = (previous == "empty" || previous != r.accno1);
+        const bool last = input->bad() || input->peek() == EOF;
+        if (last) r.new_row = true;                              // mode '9' also counts as a new first
+        r.tax1 = lookup_taxonomy(taxon_strings, r.accno1);
+        r.tax2 = lookup_taxonomy(taxon_strings, r.accno2);
+        if (!r.accno1.empty()) previous = r.accno1;
+        last_accno2 = r.accno2;
+        pairs.push_back(std::move(r));
+        if (last) break;
+    }
+    if (!opt.quiet) std::cerr << "Starting pairwise alignment." << std::endl;
+    SeqpairBatch batch;
+    Replayer rp(opt, cut_off, batch, out);
+    // accession dictionary in ascending order = the reference's map order for printed clusters
+    std::map<std::string, long> dict;
+    for (const auto &r : pairs) { dict[r.accno1] = 0; dict[r.accno2] = 0; }
+    std::vector<const std::string *> name_of;
+    for (auto &kv : dict) { kv.second = (long)name_of.size(); name_of.push_back(&kv.first); }
+    rp.clusters.reset(name_of.size());
+    std::vector<uint32_t> ia, ib;
+    for (const auto &r : pairs) {
+        ia.push_back((uint32_t)batch.add_sequence(r.seq1));
+        ib.push_back((uint32_t)batch.add_sequence(r.seq2));
+    }
+    if (opt.matrix && mode == 'd')
+        out.put("Proportion different/Similarity/Jukes-Cantor distance/Difference between JC and similarity\n");
+    pa_params params{7, -5, -15, -1, opt.aligned ? 1 : 0};
+    std::vector<pa_pair_result> recs(pairs.size());
+    if (!pairs.empty() && mode != 'C') {
+        init_devices();
+        batch.upload();
+        if (mode != 'a') batch.align_list(params, ia, ib, recs.data());
+    }
+    size_t cur = 0;
+    rp.taxon_of = [&](const PairView &, int side) { return side == 1 ? pairs[cur].tax1 : pairs[cur].tax2; };
+    // get_comp_value_pair (src/seqdatabase.cpp:22-32): non-N characters of the first sequence of the
+    // current pair whose name DIFFERS from the one asked for (the reference's test is inverted)
+    auto non_n = [](const std::string &s) { float v = 0; for (char c : s) if (c != 'n' && c != 'N') v += 1.0f; return v; };
+    rp.comp_of = [&](long which) {
+        const PairRecord &r = pairs[cur];
+        const std::string &accno = *name_of[(size_t)which];
+        if (accno != r.accno1) return non_n(r.seq1);
+        if (accno != r.accno2) return non_n(r.seq2);
+        return 0.0f;
+    };
+    for (cur = 0; cur < pairs.size(); ++cur) {
+        const PairRecord &r = pairs[cur];
+        PairView v{&r.accno1, &r.accno2, (long)ia[cur], (long)ib[cur], dict[r.accno1], dict[r.accno2], r.new_row};
+        rp.pair(v, PairStats{recs[cur]}, params);
+    }
+    if (opt.matrix && !pairs.empty() && !last_accno2.empty()) { out.put('\n'); out.put(last_accno2); out.put('\n'); }
+    if (!opt.quiet) std::cerr << std::endl;
+    if (mode == 'A' || mode == 'B') {
+        const std::string levels = rp.deviations.get_levels();
+        out.put("# Alignment groups for "); out.put(table); out.put('\n');
+        out.put("#    Alignment groups: "); out.put(levels); out.put('\n');
+        if (!opt.quiet) std::cerr << "    Aprox. mad. entire group = " << rp.deviations.approx_mad() << std::endl;
+        if (groups_file.good()) groups_file << table << "\t" << levels << std::endl;
+    }
+    if (mode == 'B' || mode == 'C') {
+        out.flush();
+        std::cout << "### Clusters " << table << ", cut-off: " << cut_off << " ###" << std::endl;
+        rp.clusters.print(std::cout, [&](long s) -> const std::string & { return *name_of[(size_t)s]; });
+        std::cout.flush();
+    }
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    Options opt;
+    // flag handling and return codes as src/pairalign.cpp:133-268 (most errors return 0)
+    for (int i = 1; i < argc; ++i) {
+        const char *a = argv[i];
+        auto is = [&](const char *s, const char *l) { return !strcmp(a, s) || !strcmp(a, l); };
+        if (is("-a", "--alignments")) opt.output_mode = 'a';
+        else if (is("-d", "--distances")) opt.output_mode = 'd';
+        else if (is("-p", "--proportion_difference")) opt.output_mode = 'p';
+        else if (is("-s", "--similarity")) opt.output_mode = 's';
+        else if (is("-j", "--jc_distance")) opt.output_mode = 'j';
+        else if (is("-i", "--difference")) opt.output_mode = 'c';
+        else if (is("-m", "--matrix")) { opt.matrix = true; if (opt.output_mode == 'a') opt.output_mode = 'p'; }
+        else if (is("-n", "--names")) opt.output_names = true;
+        else if (is("-A", "--aligned")) opt.aligned = true;
+        else if (is("-v", "--verbose")) opt.quiet = false;
+        else if (is("-T", "--threads")) {
+            ++i;
+            if (i < argc && argv[i][0] != '-') opt.n_threads = atoi(argv[i]);
+            else { std::cerr << "--threads or -T must be followed by a integer value, e.g. -T 4. Quiting quietly." << std::endl; return 0; }
+        }
+        else if (is("-f", "--file")) {
+            if (i + 1 < argc && argv[i + 1][0] != '-') opt.file_name = argv[++i];
+            else { std::cerr << "-f/--file needs to be followed by a file name." << std::endl; return 1; }
+        }
+        else if (!strcmp(a, "--format")) {
+            if (i + 1 < argc && argv[i + 1][0] != '-') {
+                ++i;
+                if (!strcmp(argv[i], "fasta")) opt.format = "fasta";
+                else if (!strcmp(argv[i], "pairfst") || !strcmp(argv[i], "pairfa")) opt.format = "pairfa";
+                else { std::cerr << argv[i] << " is not a valid option for --format. The options are pairfst, or fasta." << std::endl; return 1; }
+            } else { std::cerr << "--format require fasta or pairwise as extra argument. Use -h for more help." << std::endl; return 1; }
+        }
+        else if (is("-g", "--group")) {
+            opt.output_mode = 'A';
+            if (i + 1 < argc && argv[i + 1][0] != '-') {
+                ++i;
+                const std::vector<std::string> args = split_sub_args(argv[i], ':');
+                if (args[0] == "alignment_groups") opt.output_mode = 'A';
+                else if (args[0] == "cluster") opt.output_mode = 'C';
+                else if (args[0] == "both") opt.output_mode = 'B';
+                else {
+                    std::cerr << "Do not recognize argument '" << args[0] << "'. Options are 'alignment_groups', 'cluster', 'both'." << std::endl;
+                    return 1;
+                }
+                for (size_t k = 1; k < args.size(); ++k) {
+                    std::vector<std::string> sub = split_sub_args(args[k].c_str(), '=');
+                    const std::string &key = sub[0];
+                    const bool has_value = sub.size() > 1;
+                    auto value = [&]() { return has_value ? sub[1] : std::string(); };
+                    if ((key == "cut-off" || key == "cut_off" || key == "cutoff" || key == "cut off") && key.size() > 1) {
+                        if (!has_value) { std::cerr << "Unrecognized argument or missing value for argument given to -g/--group: " << key << "." << std::endl; return 1; }
+                        opt.cut_off = value();
+                    } else if ((key == "min-length" || key == "min_length" || key == "minlength" || key == "min length") && key.size() > 1) {
+                        if (!has_value) { std::cerr << "Unrecognized argument or missing value for argument given to -g/--group: " << key << "." << std::endl; return 1; }
+                        opt.min_length = atoi(value().c_str());
+                    } else if ((key == "taxon" || key == "taxonomy" || key == "taxon_file" || key == "taxonfile") && key.size() > 1) {
+                        if (!has_value) { std::cerr << "Unrecognized argument or missing value for argument given to -g/--group: " << key << "." << std::endl; return 1; }
+                        opt.taxonomy_file = value();
+                    } else if (key == "only_lead" || key == "only-lead" || key == "only lead" || key == "previous_clusters") {
+                        opt.only_lead = true;
+                    } else {
+                        std::cerr << "Unrecognized argument or missing value for argument given to -g/--group: " << key << "." << std::endl;
+                        return 1;
+                    }
+                }
+            }
+        }
+        else if (is("-h", "--help")) { print_help(); return 0; }
+        else if (i == argc - 1 && a[0] != '-' && opt.file_name.empty()) opt.file_name = a;
+        else {
+            std::cerr << "The program was called with the following command:" << std::endl;
+            for (int j = 0; j < argc; ++j) std::cerr << argv[j] << ' ';
+            std::cerr << std::endl;
+            std::cerr << "Argument " << a << " not recognized. For available arguments give -h or --help." << std::endl;
+            return 0;
+        }
+    }
+    if (!opt.quiet) {
+        std::cerr << "The program was called with the following command:" << std::endl;
+        for (int i = 0; i < argc; ++i) std::cerr << argv[i] << ' ';
+        std::cerr << std::endl << std::endl;
+    }
+    bool error_flag = false;
+    if (opt.min_length < 0) {
+        std::cerr << "Minimum sequence length to consider for clustering must be positive integer, e.g. 100." << std::endl;
+        error_flag = true;
+    }
+    if (opt.n_threads < 1) {
+        std::cerr << "Number of threads (--threads or -T) must be 1 or more (not " << opt.n_threads << "), e.g. 4." << std::endl;
+        error_flag = true;
+    }
+    if (error_flag) { std::cerr << "Quitting quietly." << std::endl; return 0; }
+    time_t rawtime = time(0);
+    if (!opt.quiet) std::cerr << "Started at:" << std::endl << asctime(localtime(&rawtime));
+    int rc = 0;
+    try {
+        Out out;
+        if (opt.format == "pairfa") run_pairfasta(opt, out);
+        else run_fasta(opt, out);
+        out.flush();
+    } catch (const std::exception &e) {
+        std::fflush(stdout);
+        std::cerr << "pairalign_b200: " << e.what() << std::endl;
+        rc = 2;
+    }
+    pa_shutdown();
+    rawtime = time(0);
+    if (!opt.quiet) std::cerr << "Ended at:" << std::endl << asctime(localtime(&rawtime));
+    return rc;
+}

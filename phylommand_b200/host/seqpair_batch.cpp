@@ -1,0 +1,85 @@
+#include "seqpair_batch.h"
+
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+
+namespace pab {
+
+static void check(int rc, const char *what) {
+    if (rc != PA_OK) throw std::runtime_error(std::string(what) + ": " + pa_last_error());
+}
+
+void init_devices() {
+    std::vector<int> ids;
+    if (const char *env = std::getenv("PAIRALIGN_DEVICES")) {
+        std::string s(env), tok;
+        for (size_t k = 0; k <= s.size(); ++k) {
+            if (k == s.size() || s[k] == ',') { if (!tok.empty()) ids.push_back(std::atoi(tok.c_str())); tok.clear(); }
+            else tok += s[k];
+        }
+    } else {
+        const int n = pa_visible_devices();
+        for (int k = 0; k < n; ++k) ids.push_back(k);
+    }
+    check(pa_init(ids.empty() ? nullptr : ids.data(), (int)ids.size()), "pa_init");
+}
+
+size_t SeqpairBatch::add_sequence(const std::string &raw) {
+    const size_t start = masks_.size();
+    masks_.resize(start + raw.size() + 1);
+    size_t n_unknown = 0;
+    std::string unk(raw.size(), '\0');
+    const size_t n = pa_encode_sequence(raw.data(), raw.size(), masks_.data() + start, &n_unknown,
+                                        unk.empty() ? nullptr : &unk[0], unk.size());
+    masks_.resize(start + n);
+    offsets_.push_back(masks_.size());
+    unk.resize(n_unknown);
+    if (n_unknown) any_unknown_ = true;
+    unknown_.push_back(unk);
+    return offsets_.size() - 2;
+}
+
+void SeqpairBatch::warn_unknown(size_t s) const {
+    for (char c : unknown_[s]) std::cerr << "Can not interpret '" << c << "'. Not in alphabet." << std::endl;
+}
+
+std::string SeqpairBatch::text(size_t s) const {
+    std::string out(length(s), '-');
+    const uint8_t *m = masks(s);
+    for (size_t k = 0; k < out.size(); ++k) out[k] = pa_mask_to_char(m[k]);
+    return out;
+}
+
+void SeqpairBatch::upload() {
+    check(pa_upload_sequences(masks_.data(), offsets_.data(), (uint32_t)size()), "pa_upload_sequences");
+}
+
+void SeqpairBatch::align_range(const pa_params &p, uint64_t first, uint64_t count, pa_pair_result *out) {
+    check(pa_align_all_pairs(&p, first, count, out), "pa_align_all_pairs");
+}
+
+void SeqpairBatch::align_list(const pa_params &p, const std::vector<uint32_t> &ia, const std::vector<uint32_t> &ib,
+                              pa_pair_result *out) {
+    check(pa_align_pairs(&p, ia.data(), ib.data(), ia.size(), out), "pa_align_pairs");
+}
+
+void SeqpairBatch::alignment(const pa_params &p, uint32_t a, uint32_t b, std::string &x, std::string &y) {
+    const uint32_t n = length(a), m = length(b);
+    if (p.aligned) { x = text(a); y = text(b); return; }       // pairalign -A -a prints the input back
+    if (n == 0 || m == 0) {
+        // the reference indexes outside its (empty) matrices here; what it prints in practice is the
+        // non-empty sequence against gaps
+        x = n ? text(a) : std::string(m, '-');
+        y = m ? text(b) : std::string(n, '-');
+        return;
+    }
+    std::vector<uint8_t> ax(n + m), ay(n + m);
+    uint32_t alen = 0;
+    check(pa_align_pair_traceback(&p, a, b, ax.data(), ay.data(), n + m, &alen, nullptr), "pa_align_pair_traceback");
+    x.assign(alen, '-');
+    y.assign(alen, '-');
+    for (uint32_t k = 0; k < alen; ++k) { x[k] = pa_mask_to_char(ax[k]); y[k] = pa_mask_to_char(ay[k]); }
+}
+
+}  // namespace pab
