@@ -250,7 +250,7 @@ def main() -> None:
             t = fn()
             torch.cuda.synchronize()
             el += time.perf_counter() - t0
-            kern += t["dp_fast_ms"] + t["dp_general_ms"]
+            kern += t["dp_duo_ms"] + t["dp_fast_ms"] + t["dp_general_ms"]
             launches += t["kernel_launches"]
         barrier()
         v = torch.tensor([el, kern], dtype=torch.float64, device="cuda")
@@ -304,7 +304,7 @@ def main() -> None:
             achieved = OPS_PER_CELL * my_cells / (kern_step_ms * 1e-3) / 1e9
             line["roofline"] = {
                 "bound": "int32", "achieved": achieved, "peak": alu, "unit": "Gop/s", "frac": achieved / alu, "traffic": None,
-                "kernel": "pa_warp_dp_kernel<16,false>", "kernel_ms_per_step": kern_step_ms,
+                "kernel": "pa_warp_duo_kernel<16> (s16x2, two pairs per warp)", "kernel_ms_per_step": kern_step_ms,
                 "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL,
                 "peak_source": "pa_int32_peak measured in this run: best single-pipe integer issue rate (IADD3 / VIMNMX / VIADDMNMX chains, all SMs)",
                 "measured": {k: {"gops": v[0], "sm_mhz": v[1]} for k, v in peak.items()},

@@ -79,8 +79,9 @@ typedef struct {
     uint64_t pairs;
     uint32_t kernel_launches;
     uint32_t n_devices;
-    double   dp_fast_ms;     /* the 2-bit register-wavefront kernel alone                  */
+    double   dp_fast_ms;     /* the 32-bit 2-bit register-wavefront kernel (one pair per warp) */
     double   dp_general_ms;  /* the IUPAC/gap (int32 wrap) kernel alone                    */
+    double   dp_duo_ms;      /* the s16x2 kernel (two pairs per warp); with -A: the stats kernel */
 } pa_timing;
 
 /* ---- life cycle --------------------------------------------------------- */

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,7 +20,8 @@ namespace {
 
 using namespace pa;
 
-constexpr int KFAST = 16;     // columns per lane, 2-bit path
+constexpr int KDUO = 16;      // columns per lane, s16x2 two-pairs-per-warp path
+constexpr int KFAST = 16;     // columns per lane, 32-bit 2-bit path
 constexpr int KGEN = 8;       // columns per lane, IUPAC/gap path
 constexpr uint64_t CHUNK_PAIRS = 1ull << 22;   // pairs per launch (84 MB of records)
 
@@ -51,13 +53,14 @@ struct Device {
     uint8_t *pure = nullptr;
     // scratch
     unsigned long long *counters = nullptr;   // [0] fast work counter, [1] general work counter
-    unsigned int *n_deferred = nullptr;
-    uint32_t *deferred = nullptr;
+    unsigned int *n_deferred = nullptr;       // [0] deferred by the s16x2 kernel, [1] deferred by the 32-bit kernel
+    uint32_t *deferred = nullptr, *deferred2 = nullptr;
     size_t deferred_cap = 0;
+    unsigned long long *row_items = nullptr;  // items (pairs of pairs) in rows before a; n_seq+1 entries
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_fast = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_fast = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -65,9 +68,10 @@ struct Device {
     size_t d_pairs_cap = 0;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_done[2] = {};
-    bool chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
+    bool chunk_duo = false, chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
+    cudaEvent_t ev_mid = nullptr;                 // between the s16x2 kernel and the 32-bit follow-up
     // timing accumulators of the last call
-    double fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
+    double duo_ms = 0, fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
     uint32_t launches = 0;
 };
 
@@ -79,7 +83,9 @@ struct Context {
     std::vector<uint64_t> pref;        // pref[s] = sum of len[0..s)
     std::vector<double> row_cells;     // cells in rows before r (double is exact enough for balancing)
     std::vector<unsigned __int128> row_cells_exact;
+    std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
+    bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
     uint32_t max_len = 0;
     pa_timing timing = {};
 };
@@ -91,7 +97,9 @@ void free_device(Device &d) {
     if (d.id < 0) return;
     cudaSetDevice(d.id);
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
-    cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.bbuf);
+    cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.bbuf);
+    cudaFree(d.row_items);
+    if (d.ev_mid) cudaEventDestroy(d.ev_mid);
     for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
     cudaFree(d.d_ia); cudaFree(d.d_ib);
     for (auto &e : d.ev) if (e) cudaEventDestroy(e);
@@ -144,90 +152,109 @@ int ensure_out(Device &d, size_t n) {
 
 int ensure_deferred(Device &d, size_t n) {
     if (n <= d.deferred_cap) return PA_OK;
-    if (d.deferred) cudaFree(d.deferred);
-    d.deferred = nullptr; d.deferred_cap = 0;
+    cudaFree(d.deferred); cudaFree(d.deferred2);
+    d.deferred = d.deferred2 = nullptr; d.deferred_cap = 0;
     CU(cudaMalloc(&d.deferred, n * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.deferred2, n * sizeof(uint32_t)));
     d.deferred_cap = n;
     return PA_OK;
 }
 
-// The general kernel reads its item count from device memory (n_deferred), so
-// no host round trip sits between the two launches.
-template <int K>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pa_general_deferred_kernel(const SeqStore S, const Scoring sc, PairSource src, const unsigned int *n_items,
-                           unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
-                           pa_pair_result *out) {
-    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
-    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
-    const unsigned long long count = *n_items;
-    for (;;) {
-        unsigned long long w = 0;
-        if (lane == 0) w = atomicAdd(work_counter, 1ull);
-        w = __shfl_sync(FULL_MASK, w, 0);
-        if (w >= count) break;
-        const uint64_t e = src.idx[w];
-        uint32_t a, b;
-        if (src.ia) { a = src.ia[e]; b = src.ib[e]; }
-        else tri_pair(src.first + e, S.n_seq, a, b);
-        const int n = (int)S.len[a], m = (int)S.len[b];
-        __syncwarp();
-        const uint32_t *xs = stage_seq(S.p4 + S.off4[a], (uint32_t)(n + 7) >> 3, stage[wib][0], lane);
-        const uint32_t *ys = stage_seq(S.p4 + S.off4[b], (uint32_t)(m + 7) >> 3, stage[wib][1], lane);
-        __syncwarp();
-        align_warp<K, true>(xs, n, ys, m, sc, bbuf, &out[e], lane);
-    }
+// Longest sequence the s16x2 kernel may take: every score must stay inside int16.
+uint32_t max_len16(const pa_params &p) {
+    const long long m = p.match > 0 ? p.match : 1;
+    const long long ge = p.gap_ext < 0 ? -(long long)p.gap_ext : 1;
+    const long long fixed = std::llabs((long long)p.mismatch) + std::llabs((long long)p.gap_open);
+    long long a = 32000 / m, b = (32000 - fixed) / ge;
+    long long r = std::min(a, b);
+    if (r < 0) r = 0;
+    return (uint32_t)std::min<long long>(r, 8192);
 }
 
 // Launch the kernels for `count` elements (triangle range starting at `first`,
 // or the explicit lists ia/ib) writing records to d_out (device).  Asynchronous
 // on d.stream; events ev[0..3] bracket the two DP kernels.
+// item (pair of pairs) that holds triangle index q
+uint64_t item_of(const Context &c, uint64_t q) {
+    uint32_t a, b;
+    tri_pair(q, c.n_seq, a, b);
+    return c.row_items[a] + (uint64_t)(b - a - 1) / 2;
+}
+
+// Launch the kernels for `count` elements (triangle range starting at `first`,
+// or the explicit lists ia/ib) writing records to d_out (device).  Asynchronous
+// on d.stream.  Stages (each later stage takes what the previous one deferred,
+// its item count read from device memory):
+//   1. s16x2 kernel, two pairs per warp      triangle ranges, A/C/G/T, len <= max_len16
+//   2. 32-bit 2-bit kernel, one pair per warp longer A/C/G/T pairs, explicit pair lists
+//   3. general kernel                         IUPAC sets, '-', any scoring parameters
+// Events: ev[0]..ev[1] stage 1, ev[1]..ev_mid stage 2, ev[2]..ev[3] stage 3.
 int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
                  const uint32_t *d_ia, const uint32_t *d_ib, pa_pair_result *d_out) {
     const SeqStore S = store_of(d, c.n_seq);
     Scoring sc{p.match, p.mismatch, p.gap_open, p.gap_ext};
     PairSource src{first, d_ia, d_ib, nullptr};
-    CU(cudaMemsetAsync(d.counters, 0, 2 * sizeof(unsigned long long), d.stream));
-    CU(cudaMemsetAsync(d.n_deferred, 0, sizeof(unsigned int), d.stream));
-    d.chunk_fast = d.chunk_gen = false;
+    CU(cudaMemsetAsync(d.counters, 0, 3 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.n_deferred, 0, 2 * sizeof(unsigned int), d.stream));
+    d.chunk_duo = d.chunk_fast = d.chunk_gen = false;
+    const int threads = WARPS_PER_CTA * 32;
     if (p.aligned) {
-        d.chunk_fast = true;
+        d.chunk_duo = true;
         CU(cudaEventRecord(d.ev[0], d.stream));
-        pa_aligned_stats_kernel<<<d.grid_stats, WARPS_PER_CTA * 32, 0, d.stream>>>(S, src, count, d.counters, d_out);
+        pa_aligned_stats_kernel<<<d.grid_stats, threads, 0, d.stream>>>(S, src, count, d.counters, d_out);
         CU(cudaGetLastError());
         CU(cudaEventRecord(d.ev[1], d.stream));
+        CU(cudaEventRecord(d.ev_mid, d.stream));
         CU(cudaEventRecord(d.ev[2], d.stream));
         CU(cudaEventRecord(d.ev[3], d.stream));
         d.launches += 1;
         return PA_OK;
     }
     const bool fast = fast_params_ok(p);
+    const uint32_t l16 = fast ? max_len16(p) : 0;
+    const bool duo = fast && !d_ia && l16 >= 16 && !c.force_32bit;
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;
     CU(cudaEventRecord(d.ev[0], d.stream));
-    if (fast) {
-        pa_warp_dp_kernel<KFAST, false><<<d.grid_fast, WARPS_PER_CTA * 32, 0, d.stream>>>(
-            S, sc, src, count, d.counters, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
+    bool stage2 = false, stage3 = false;
+    PairSource src2 = src;
+    const unsigned int *count2 = nullptr;
+    if (duo) {
+        const uint64_t item_lo = item_of(c, first), item_hi = item_of(c, first + count - 1) + 1;
+        pa_warp_duo_kernel<KDUO><<<d.grid_duo, threads, 0, d.stream>>>(
+            S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+            d.deferred, d.n_deferred);
+        CU(cudaGetLastError());
+        d.launches += 1;
+        d.chunk_duo = true;
+        stage2 = !c.all_pure || c.max_len > l16;       // something may have been deferred
+        src2.idx = d.deferred;
+        count2 = d.n_deferred;
+    } else if (fast) {
+        stage2 = true;
+    }
+    CU(cudaEventRecord(d.ev[1], d.stream));
+    if (stage2) {
+        pa_warp_dp_kernel<KFAST, false><<<d.grid_fast, threads, 0, d.stream>>>(
+            S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_fast = true;
+        stage3 = !c.all_pure;
     }
-    CU(cudaEventRecord(d.ev[1], d.stream));
+    CU(cudaEventRecord(d.ev_mid, d.stream));
     CU(cudaEventRecord(d.ev[2], d.stream));
     if (!fast) {
-        pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, WARPS_PER_CTA * 32, 0, d.stream>>>(
-            S, sc, src, count, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred, d.n_deferred);
+        pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, threads, 0, d.stream>>>(
+            S, sc, src, count, nullptr, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_gen = true;
-    } else if (!c.all_pure) {
-        PairSource s2 = src;
-        s2.idx = d.deferred;
-        pa_general_deferred_kernel<KGEN><<<d.grid_gen, WARPS_PER_CTA * 32, 0, d.stream>>>(
-            S, sc, s2, d.n_deferred, d.counters + 1, d.bbuf, d.bbuf_rows, d_out);
+    } else if (stage3) {
+        PairSource src3 = src;
+        src3.idx = d.deferred2;
+        pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, threads, 0, d.stream>>>(
+            S, sc, src3, count, d.n_deferred + 1, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_gen = true;
@@ -239,6 +266,8 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
 int collect_chunk_times(Device &d) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+    if (d.chunk_duo) d.duo_ms += ms;
+    CU(cudaEventElapsedTime(&ms, d.ev[1], d.ev_mid));
     if (d.chunk_fast) d.fast_ms += ms;
     CU(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]));
     if (d.chunk_gen) d.gen_ms += ms;
@@ -252,7 +281,7 @@ int collect_chunk_times(Device &d) {
 int run_range(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
               const uint32_t *h_ia, const uint32_t *h_ib, pa_pair_result *out, pa_pair_result *d_resident) {
     CU(cudaSetDevice(d.id));
-    d.fast_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
+    d.duo_ms = d.fast_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
     d.launches = 0;
     if (count == 0) return PA_OK;
     const uint64_t chunk = std::min<uint64_t>(CHUNK_PAIRS, count);
@@ -358,19 +387,19 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
         for (auto &ev : d.ev) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
         for (auto &ev : d.ev_done) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 2 * sizeof(unsigned long long));
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, sizeof(unsigned int));
+        if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_mid);
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 3 * sizeof(unsigned long long));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 2 * sizeof(unsigned int));
         int occ = 0;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KFAST, false>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
         d.grid_gen = std::max(1, occ) * d.n_sm;
-        int occ2 = 0;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pa_general_deferred_kernel<KGEN>, WARPS_PER_CTA * 32, 0);
-        d.grid_gen = std::min(d.grid_gen, std::max(1, occ2) * d.n_sm);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(d.grid_fast, d.grid_gen) * WARPS_PER_CTA;
+        d.n_warps = (uint32_t)std::max(d.grid_duo, std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA;
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -378,6 +407,7 @@ int pa_init(const int *devices, int n_dev) {
             return fail(PA_ECUDA, "device %d setup failed: %s", d.id, msg.c_str());
         }
     }
+    if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     g_ctx = c;
     return PA_OK;
 }
@@ -480,11 +510,16 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     for (uint32_t r = 0; r + 1 < n_seq; ++r)
         c.row_cells_exact[r + 1] = c.row_cells_exact[r] + (unsigned __int128)len[r] * (c.pref[n_seq] - c.pref[r + 1]);
     if (n_seq) c.row_cells_exact[n_seq] = c.row_cells_exact[n_seq - 1];
+    c.row_items.assign((size_t)n_seq + 1, 0);
+    for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
 
     for (auto &d : c.dev) {
         CU(cudaSetDevice(d.id));
         cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure); cudaFree(d.bbuf);
-        d.p2 = d.p4 = d.off2 = d.off4 = d.len = nullptr; d.pure = nullptr; d.bbuf = nullptr;
+        cudaFree(d.row_items);
+        d.p2 = d.p4 = d.off2 = d.off4 = d.len = nullptr; d.pure = nullptr; d.bbuf = nullptr; d.row_items = nullptr;
+        CU(cudaMalloc(&d.row_items, c.row_items.size() * sizeof(unsigned long long)));
+        CU(cudaMemcpy(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&d.p2, p2.size() * 4));
         CU(cudaMalloc(&d.p4, p4.size() * 4));
         CU(cudaMalloc(&d.off2, std::max<size_t>(n_seq, 1) * 4));
@@ -604,7 +639,8 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
         const Device &d = c.dev[p];
-        tm.kernel_ms = std::max(tm.kernel_ms, d.fast_ms + d.gen_ms);
+        tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.gen_ms);
+        tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);
         tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
         tm.dp_general_ms = std::max(tm.dp_general_ms, d.gen_ms);
         tm.d2h_ms = std::max(tm.d2h_ms, d.d2h_ms);

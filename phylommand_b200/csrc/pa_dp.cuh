@@ -285,6 +285,174 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
     }
 }
 
+// ---------------------------------------------------------------------------
+// Two pairs (x, y1) and (x, y2) that share the row sequence on one warp, packed
+// as signed 16-bit halves of every score register (low half = pair 1, high half
+// = pair 2) and computed with the s16x2 DPX instructions of sm_100a
+// (VIMNMX3.S16x2, VIADDMNMX.S16x2, VIADD.16x2, and VIMNMX.S16x2 with its two
+// predicate outputs for the move).  The (columns, mismatches) counters stay 32
+// bit per pair.  Valid while every score fits int16 (host checks:
+// match*len <= 32000 and |gap_ext|*len + |mismatch| + |gap_open| <= 32000).
+//
+// Both column sets are right-aligned in the same P*32*K slots, so pad columns
+// (a fixed point of the recurrence, see align_warp) absorb the length
+// difference and the last column of BOTH pairs is lane 31's last slot.
+// Score table bytes: 0-3 base codes, 4 column 0 of pair 1, 5 zero (pad),
+// 6 column 0 of pair 2.  Increment table bytes: 0-3 mismatch flag per base code,
+// 4 column-0 flag pair 1, 5 zero, 6 one, 7 column-0 flag pair 2.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+template <int K>
+__device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
+                                               const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
+                                               pa_pair_result *res1, pa_pair_result *res2, const int lane) {
+    constexpr int W = 32 * K;
+    const int mmax = m1 > m2 ? m1 : m2;
+    const int P = (mmax + W - 1) / W;
+    const int pad1 = P * W - m1, pad2 = P * W - m2;
+    const int Hinit = -sc.go;
+    const uint32_t HinitPk = pack16(Hinit, Hinit);
+    const uint32_t GOpk = pack16(sc.go, sc.go), GEpk = pack16(sc.ge, sc.ge);
+
+    int rowBest1 = INT_MIN, rowJ1 = 0, rowBest2 = INT_MIN, rowJ2 = 0;
+    uint32_t rowC1 = 0, rowC2 = 0;
+    int colBest1 = INT_MIN, colI1 = n - 1, colBest2 = INT_MIN, colI2 = n - 1;
+    uint32_t colC1 = 0, colC2 = 0;
+
+    const uint32_t y10 = fetch2(ys1, 0), y20 = fetch2(ys2, 0);
+    const uint32_t Mn = (uint32_t)sc.match & 0xffu, Xn = (uint32_t)sc.mismatch & 0xffu;
+    const uint32_t Mz = (uint32_t)(sc.match + sc.go) & 0xffu, Xz = (uint32_t)(sc.mismatch + sc.go) & 0xffu;
+    const uint32_t baseN = Xn * 0x01010101u, dN = Mn ^ Xn;
+    const uint32_t baseZ = Xz * 0x01010101u, dZ = Mz ^ Xz;
+
+    for (int p = 0; p < P; ++p) {
+        const int s0 = p * W + lane * K;           // slot of this lane's k = 0
+        uint32_t H[K], Gy[K], C1[K], C2[K], selS[K], selI1[K], selI2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
+            H[k] = HinitPk; Gy[k] = 0; C1[k] = 0; C2[k] = 0;
+            uint32_t c1, c2, i1, i2;
+            if (j1 < 0)       { c1 = 5; i1 = 0x5555u; }
+            else if (j1 == 0) { c1 = 4; i1 = 0x5654u; }
+            else              { c1 = fetch2(ys1, j1); i1 = 0x5650u | c1; }
+            if (j2 < 0)       { c2 = 5; i2 = 0x5555u; }
+            else if (j2 == 0) { c2 = 6; i2 = 0x5657u; }
+            else              { c2 = fetch2(ys2, j2); i2 = 0x5650u | c2; }
+            selS[k] = ((8u | c2) << 12) | (c2 << 8) | ((8u | c1) << 4) | c1;
+            selI1[k] = i1; selI2[k] = i2;
+        }
+        uint32_t hprev = HinitPk, c1prev = 0, c2prev = 0;
+        uint32_t Hout = HinitPk, Gxout = 0, c1out = 0, c2out = 0;
+        int4 nxt = make_int4((int)HinitPk, 0, 0, 0);
+        if (p > 0 && lane == 0) nxt = __ldcg(&bbuf[0]);
+        uint32_t xcur = 0, xprev = 0;
+        if (lane < n) xcur = fetch2(xs, lane);
+
+        const int T = n + 31;
+        for (int t = 0; t < T; ++t) {
+            const int r = t & 31;
+            if (r == 0 && t > 0) {
+                xprev = xcur;
+                const int ii = t + lane;
+                xcur = 0;
+                if (ii < n) xcur = fetch2(xs, ii);
+            }
+            const uint32_t xv = (lane <= r) ? xcur : xprev;
+            const uint32_t xi = __shfl_sync(FULL_MASK, xv, (r - lane) & 31);
+            uint32_t hin = __shfl_up_sync(FULL_MASK, Hout, 1);
+            uint32_t gin = __shfl_up_sync(FULL_MASK, Gxout, 1);
+            uint32_t c1in = __shfl_up_sync(FULL_MASK, c1out, 1);
+            uint32_t c2in = __shfl_up_sync(FULL_MASK, c2out, 1);
+            if (lane == 0) {
+                hin = (uint32_t)nxt.x; gin = (uint32_t)nxt.y; c1in = (uint32_t)nxt.z; c2in = (uint32_t)nxt.w;
+                if (p > 0 && t + 1 < n) nxt = __ldcg(&bbuf[t + 1]);
+            }
+            const int i = t - lane;
+            if (i >= 0 && i < n) {
+                const uint32_t sh = xi * 8u;
+                const bool z = (i == 0);
+                const uint32_t Rlo = (z ? baseZ : baseN) ^ ((z ? dZ : dN) << sh);
+                const uint32_t Rhi = ((xi == y10) ? Mz : Xz) | (((xi == y20) ? Mz : Xz) << 16);
+                const uint32_t Mlo = 0x01010101u ^ (1u << sh);
+                const uint32_t Mhi = 0x00010000u | (xi != y10 ? 1u : 0u) | (xi != y20 ? 0x01000000u : 0u);
+                uint32_t Hd = hprev, Gl = gin, cd1 = c1prev, cd2 = c2prev, cl1 = c1in, cl2 = c2in;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t s = prmt(Rlo, Rhi, selS[k]);
+                    const uint32_t inc1 = prmt(Mlo, Mhi, selI1[k]);
+                    const uint32_t inc2 = prmt(Mlo, Mhi, selI2[k]);
+                    const uint32_t Gu = Gy[k];
+                    const uint32_t cu1 = C1[k], cu2 = C2[k];
+                    const uint32_t h = __vadd2(__vimax3_s16x2(Hd, Gu, Gl), s);
+                    const uint32_t o = __vadd2(Hd, GOpk);
+                    const uint32_t gy = __viaddmax_s16x2(Gu, GEpk, o);
+                    const uint32_t gx = __viaddmax_s16x2(Gl, GEpk, o);
+                    bool pUhi, pUlo, pDhi, pDlo;
+                    const uint32_t g = __vibmax_s16x2(gy, gx, &pUhi, &pUlo);     // gy >= gx
+                    (void)__vibmax_s16x2(h, g, &pDhi, &pDlo);                    // h >= max(gy, gx)
+                    const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
+                    const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
+                    const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
+                    Hd = H[k]; cd1 = cu1; cd2 = cu2;
+                    H[k] = h; Gy[k] = gy; C1[k] = c1; C2[k] = c2;
+                    Gl = gx; cl1 = c1; cl2 = c2;
+                }
+                hprev = hin; c1prev = c1in; c2prev = c2in;
+                Hout = H[K - 1]; Gxout = Gl; c1out = cl1; c2out = cl2;
+                if (lane == 31) {
+                    if (p < P - 1) {
+                        __stcg(&bbuf[i], make_int4((int)Hout, (int)Gxout, (int)c1out, (int)c2out));
+                    } else {
+                        const int h1 = lo16(Hout), h2 = hi16(Hout);
+                        if (h1 > colBest1) { colBest1 = h1; colI1 = i; colC1 = c1out; }
+                        if (h2 > colBest2) { colBest2 = h2; colI2 = i; colC2 = c2out; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        int bv1 = INT_MIN, bj1 = INT_MAX, bv2 = INT_MIN, bj2 = INT_MAX;
+        uint32_t bc1 = 0, bc2 = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
+            const int h1 = lo16(H[k]), h2 = hi16(H[k]);
+            if (j1 >= 0 && h1 > bv1) { bv1 = h1; bj1 = j1; bc1 = C1[k]; }
+            if (j2 >= 0 && h2 > bv2) { bv2 = h2; bj2 = j2; bc2 = C2[k]; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int ov1 = __shfl_xor_sync(FULL_MASK, bv1, d), oj1 = __shfl_xor_sync(FULL_MASK, bj1, d);
+            const uint32_t oc1 = __shfl_xor_sync(FULL_MASK, bc1, d);
+            if (ov1 > bv1 || (ov1 == bv1 && oj1 < bj1)) { bv1 = ov1; bj1 = oj1; bc1 = oc1; }
+            const int ov2 = __shfl_xor_sync(FULL_MASK, bv2, d), oj2 = __shfl_xor_sync(FULL_MASK, bj2, d);
+            const uint32_t oc2 = __shfl_xor_sync(FULL_MASK, bc2, d);
+            if (ov2 > bv2 || (ov2 == bv2 && oj2 < bj2)) { bv2 = ov2; bj2 = oj2; bc2 = oc2; }
+        }
+        if (bj1 != INT_MAX && bv1 > rowBest1) { rowBest1 = bv1; rowJ1 = bj1; rowC1 = bc1; }
+        if (bj2 != INT_MAX && bv2 > rowBest2) { rowBest2 = bv2; rowJ2 = bj2; rowC2 = bc2; }
+    }
+    colBest1 = __shfl_sync(FULL_MASK, colBest1, 31); colI1 = __shfl_sync(FULL_MASK, colI1, 31); colC1 = __shfl_sync(FULL_MASK, colC1, 31);
+    colBest2 = __shfl_sync(FULL_MASK, colBest2, 31); colI2 = __shfl_sync(FULL_MASK, colI2, 31); colC2 = __shfl_sync(FULL_MASK, colC2, 31);
+    if (lane == 0) {
+        pa_pair_result o;
+        if (res1) {
+            if (rowBest1 > colBest1) { o.score = rowBest1; o.end_i = n - 1; o.end_j = rowJ1; o.dist = rowC1 & 0xffffu; o.len = rowC1 >> 16; }
+            else                     { o.score = colBest1; o.end_i = colI1; o.end_j = m1 - 1; o.dist = colC1 & 0xffffu; o.len = colC1 >> 16; }
+            *res1 = o;
+        }
+        if (res2) {
+            if (rowBest2 > colBest2) { o.score = rowBest2; o.end_i = n - 1; o.end_j = rowJ2; o.dist = rowC2 & 0xffffu; o.len = rowC2 >> 16; }
+            else                     { o.score = colBest2; o.end_i = colI2; o.end_j = m2 - 1; o.dist = colC2 & 0xffffu; o.len = colC2 >> 16; }
+            *res2 = o;
+        }
+    }
+}
+
 // Coalesced 128-bit staging of one packed sequence into this warp's shared
 // buffer; returns the pointer to read codes from (global if it does not fit).
 __device__ __forceinline__ const uint32_t *stage_seq(const uint32_t *g, uint32_t n_words, uint32_t *sm, int lane) {
@@ -299,16 +467,20 @@ __device__ __forceinline__ const uint32_t *stage_seq(const uint32_t *g, uint32_t
 // Persistent warps pull pair indices from a global counter.
 //   !GENERAL: pairs with a non-A/C/G/T sequence are appended to `deferred`
 //             and handled by the GENERAL instantiation afterwards.
+//   count_dev != nullptr: the number of work items is read from device memory
+//             (a list another kernel of the same call has just written).
 template <int K, bool GENERAL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, const uint64_t count,
-                  unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
-                  pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
+pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, const uint64_t count_host,
+                  const unsigned int *count_dev, unsigned long long *work_counter, int4 *bbuf_all,
+                  const uint32_t bbuf_rows, pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
     int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    // the item count of a follow-up launch is whatever the previous kernel deferred (no host round trip)
+    const uint64_t count = count_dev ? (uint64_t)*count_dev : count_host;
 
     for (;;) {
         unsigned long long w = 0;
@@ -341,6 +513,71 @@ pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, cons
         }
         __syncwarp();
         align_warp<K, GENERAL>(xs, n, ys, m, sc, bbuf, &out[e], lane);
+    }
+}
+
+// Triangle range with pairs taken two at a time.  Work item u of row a covers the
+// pairs (a, a+1+2u) and (a, a+2+2u); row_item_start[a] = items in rows before a
+// (host-computed prefix, N+1 entries).  Items [item_lo, item_hi) are processed;
+// a pair is written only if its triangle index lies in [first, first+count).
+// Pairs the s16x2 path cannot take (a non-A/C/G/T sequence, or longer than
+// max_len16) are appended to `deferred` as range-relative indices.
+template <int K>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
+                   const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
+                   const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
+                   pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
+    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    const uint32_t N = S.n_seq;
+    const uint64_t n_items = item_hi - item_lo;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1ull);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= n_items) break;
+        const uint64_t item = item_lo + w;
+        // row a: last row with row_item_start[a] <= item
+        uint32_t lo = 0, hi = N - 1;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (row_item_start[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t a = lo;
+        const uint32_t u = (uint32_t)(item - row_item_start[a]);
+        const uint32_t b1 = a + 1 + 2 * u;
+        uint32_t b2 = b1 + 1;
+        const uint64_t q1 = tri_row_start(a, N) + 2ull * u;
+        bool use1 = (q1 >= first && q1 < first + count);
+        bool use2 = (b2 < N) && (q1 + 1 >= first && q1 + 1 < first + count);
+        if (b2 >= N) b2 = b1;
+        const int n = (int)S.len[a], m1 = (int)S.len[b1], m2 = (int)S.len[b2];
+        // pairs this path cannot take go to the general / 32-bit kernels
+        const bool okx = S.pure[a] && n > 0 && (uint32_t)n <= max_len16;
+        const bool ok1 = okx && S.pure[b1] && m1 > 0 && (uint32_t)m1 <= max_len16;
+        const bool ok2 = okx && S.pure[b2] && m2 > 0 && (uint32_t)m2 <= max_len16;
+        if (lane == 0) {
+            if (use1 && !ok1) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 - first);
+            if (use2 && !ok2) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 + 1 - first);
+        }
+        use1 = use1 && ok1;
+        use2 = use2 && ok2;
+        if (!use1 && !use2) continue;
+        // a half that is not wanted mirrors the other one
+        const uint32_t y1 = use1 ? b1 : b2, y2 = use2 ? b2 : b1;
+        const int my1 = use1 ? m1 : m2, my2 = use2 ? m2 : m1;
+        __syncwarp();
+        const uint32_t *xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
+        const uint32_t *ys1 = stage_seq(S.p2 + S.off2[y1], (uint32_t)(my1 + 15) >> 4, stage[wib][1], lane);
+        const uint32_t *ys2 = stage_seq(S.p2 + S.off2[y2], (uint32_t)(my2 + 15) >> 4, stage[wib][2], lane);
+        __syncwarp();
+        align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf,
+                          use1 ? &out[q1 - first] : nullptr, use2 ? &out[q1 + 1 - first] : nullptr, lane);
     }
 }
 

@@ -74,8 +74,15 @@ def test_all_pairs_pure_acgt(gpu, oracle, lo, hi, n, seed):
     enc = [synth.to_masks(s) for s in seqs]
     gpu.upload(enc)
     got = gpu.align_all_pairs()
-    assert gpu.timing()["dp_general_ms"] == 0.0     # nothing deferred to the general kernel
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_general_ms"] == 0.0   # s16x2 kernel only
     _same(got, _oracle_all(oracle, enc))
+    # the same pairs as an explicit list run on the 32-bit one-pair-per-warp kernel
+    ab = np.array([gpu.pair_from_index(k) for k in range(len(got))])
+    got32 = gpu.align_pairs(ab[:, 0], ab[:, 1])
+    t = gpu.timing()
+    assert t["dp_duo_ms"] == 0.0 and t["dp_fast_ms"] > 0
+    assert got32.tobytes() == got.tobytes()
 
 
 @pytest.mark.parametrize("iupac,gaps,lo,hi,n,seed", [(0.05, 0.0, 1, 60, 40, 5), (0.03, 0.0, 200, 300, 16, 6),
@@ -97,7 +104,7 @@ def test_mixed_pure_and_ambiguous(gpu, oracle):
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     t = gpu.timing()
-    assert t["dp_fast_ms"] > 0 and t["dp_general_ms"] > 0
+    assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] > 0
     _same(got, _oracle_all(oracle, enc))
 
 
@@ -210,3 +217,18 @@ def test_long_pair_many_passes(gpu, oracle):
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     assert tuple(got[0]) == tuple(oracle.align_forward(enc[0], enc[1]))
+
+
+def test_s16x2_kernel_near_its_int16_limit(gpu, oracle):
+    """4.5 kb sequences: scores reach 31,500 (identical pair) and stay inside int16; longer ones fall back to 32 bit."""
+    _, seqs = synth.make_long(3, 77, length=4450, spread=0.02, div_lo=0.0, div_hi=0.05)
+    enc = [synth.to_masks(s) for s in seqs]
+    enc.append(enc[0].copy())                       # identical to sequence 0: the highest possible score
+    _, longer = synth.make_long(1, 78, length=4700, spread=0.0)
+    enc.append(synth.to_masks(longer[0]))           # above max_len16 = 4571: deferred to the 32-bit kernel
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] > 0
+    _same(got, _oracle_all(oracle, enc))
+    assert int(got[2]["score"]) == 7 * len(enc[0])  # pair (0, 3)
