@@ -20,7 +20,7 @@ namespace {
 
 using namespace pa;
 
-constexpr int KDUO = 16;      // columns per lane, s16x2 two-pairs-per-warp path
+constexpr int KDUO = 12;      // columns per lane, s16x2 two-pairs-per-warp path
 constexpr int KFAST = 16;     // columns per lane, 32-bit 2-bit path
 constexpr int KGEN = 8;       // columns per lane, IUPAC/gap path
 constexpr uint64_t CHUNK_PAIRS = 1ull << 22;   // pairs per launch (84 MB of records)
@@ -534,7 +534,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
             CU(cudaMemcpy(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
             CU(cudaMemcpy(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice));
         }
-        d.bbuf_rows = std::max<uint32_t>(max_len, 1);
+        d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
         CU(cudaMalloc(&d.bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
     }
     return PA_OK;

@@ -305,9 +305,52 @@ __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
+// One row of the packed recurrence over this lane's K columns.  Reads the
+// previous row from (Hs, C1s, C2s), writes this row to (Hd, C1d, C2d); Gy is
+// updated in place.  Source and destination arrays are different registers
+// (the caller ping-pongs two rows per step), so nothing has to be copied to
+// keep H(i-1,j-1) / cnt(i-1,j-1) alive for the next column.
+template <int K>
+__device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
+                                        const uint32_t (&C1s)[K], uint32_t (&C1d)[K],
+                                        const uint32_t (&C2s)[K], uint32_t (&C2d)[K],
+                                        const uint32_t (&selS)[K], const uint32_t (&selI1)[K], const uint32_t (&selI2)[K],
+                                        const uint32_t Rlo, const uint32_t Rhi, const uint32_t Mlo, const uint32_t Mhi,
+                                        const uint32_t GOpk, const uint32_t GEpk,
+                                        uint32_t hdiag, uint32_t Gl, uint32_t cd1, uint32_t cd2, uint32_t cl1, uint32_t cl2,
+                                        uint32_t &Hout, uint32_t &Gxout, uint32_t &c1out, uint32_t &c2out) {
+    uint32_t Hdg = hdiag;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t s = prmt(Rlo, Rhi, selS[k]);
+        const uint32_t inc1 = prmt(Mlo, Mhi, selI1[k]);
+        const uint32_t inc2 = prmt(Mlo, Mhi, selI2[k]);
+        const uint32_t Gu = Gy[k];
+        const uint32_t cu1 = C1s[k], cu2 = C2s[k];
+        const uint32_t h = __vadd2(__vimax3_s16x2(Hdg, Gu, Gl), s);
+        const uint32_t o = __vadd2(Hdg, GOpk);
+        const uint32_t gy = __viaddmax_s16x2(Gu, GEpk, o);
+        const uint32_t gx = __viaddmax_s16x2(Gl, GEpk, o);
+        bool pUhi, pUlo, pDhi, pDlo;
+        const uint32_t g = __vibmax_s16x2(gy, gx, &pUhi, &pUlo);     // gy >= gx
+        (void)__vibmax_s16x2(h, g, &pDhi, &pDlo);                    // h >= max(gy, gx)
+        const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
+        const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
+        const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
+        Hdg = Hs[k]; cd1 = cu1; cd2 = cu2;
+        Hd[k] = h; Gy[k] = gy; C1d[k] = c1; C2d[k] = c2;
+        Gl = gx; cl1 = c1; cl2 = c2;
+    }
+    Hout = Hd[K - 1]; Gxout = Gl; c1out = cl1; c2out = cl2;
+}
+
+// tab: this warp's 8-entry shared table, tab[z*4 + x] = (Rlo, Rhi, Mlo, Mhi) for row code x, z = 1 for
+// row 0 (scores carry +GO there).  vrow: index of the spare scratch row that holds the virtual column
+// left of column 0, so that pass 0 and later passes feed lane 0 through the same loads.
 template <int K>
 __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
                                                const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
+                                               const uint32_t vrow, int4 *tab,
                                                pa_pair_result *res1, pa_pair_result *res2, const int lane) {
     constexpr int W = 32 * K;
     const int mmax = m1 > m2 ? m1 : m2;
@@ -319,22 +362,41 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
 
     int rowBest1 = INT_MIN, rowJ1 = 0, rowBest2 = INT_MIN, rowJ2 = 0;
     uint32_t rowC1 = 0, rowC2 = 0;
-    int colBest1 = INT_MIN, colI1 = n - 1, colBest2 = INT_MIN, colI2 = n - 1;
+    // last-column maxima of both pairs, packed like the scores; -32768 stands for "nothing yet"
+    uint32_t colBestPk = 0x80008000u;
+    int colI1 = n - 1, colI2 = n - 1;
     uint32_t colC1 = 0, colC2 = 0;
 
-    const uint32_t y10 = fetch2(ys1, 0), y20 = fetch2(ys2, 0);
-    const uint32_t Mn = (uint32_t)sc.match & 0xffu, Xn = (uint32_t)sc.mismatch & 0xffu;
-    const uint32_t Mz = (uint32_t)(sc.match + sc.go) & 0xffu, Xz = (uint32_t)(sc.mismatch + sc.go) & 0xffu;
-    const uint32_t baseN = Xn * 0x01010101u, dN = Mn ^ Xn;
-    const uint32_t baseZ = Xz * 0x01010101u, dZ = Mz ^ Xz;
+    {   // score / increment tables of this (x, y1, y2): one entry per row code and row-0 flag
+        const uint32_t y10 = fetch2(ys1, 0), y20 = fetch2(ys2, 0);
+        if (lane < 8) {
+            const uint32_t xi = lane & 3u, z = lane >> 2;
+            const int adj = z ? sc.go : 0;
+            const uint32_t Mb = (uint32_t)(sc.match + adj) & 0xffu, Xb = (uint32_t)(sc.mismatch + adj) & 0xffu;
+            const uint32_t Mz = (uint32_t)(sc.match + sc.go) & 0xffu, Xz = (uint32_t)(sc.mismatch + sc.go) & 0xffu;
+            const uint32_t sh = xi * 8u;
+            int4 e;
+            e.x = (int)((Xb * 0x01010101u) ^ ((Mb ^ Xb) << sh));
+            e.y = (int)(((xi == y10) ? Mz : Xz) | (((xi == y20) ? Mz : Xz) << 16));
+            e.z = (int)(0x01010101u ^ (1u << sh));
+            e.w = (int)(0x00010000u | (xi != y10 ? 1u : 0u) | (xi != y20 ? 0x01000000u : 0u));
+            tab[z * 4 + xi] = e;
+        }
+        if (lane == 0) __stcg(&bbuf[vrow], make_int4((int)HinitPk, 0, 0, 0));
+        __syncwarp();
+    }
+    const int n_steps = ((n + 1) >> 1) + 31;        // two rows per step, lanes one step apart
+    const int x_last_word = (n - 1) >> 4;
 
     for (int p = 0; p < P; ++p) {
+        const bool last_pass = (p == P - 1);
         const int s0 = p * W + lane * K;           // slot of this lane's k = 0
-        uint32_t H[K], Gy[K], C1[K], C2[K], selS[K], selI1[K], selI2[K];
+        // X: the odd row (2u-1, then 2u+1), Y: the even row 2u
+        uint32_t HX[K], HY[K], Gy[K], C1X[K], C1Y[K], C2X[K], C2Y[K], selS[K], selI1[K], selI2[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
-            H[k] = HinitPk; Gy[k] = 0; C1[k] = 0; C2[k] = 0;
+            HX[k] = HinitPk; HY[k] = HinitPk; Gy[k] = 0; C1X[k] = 0; C2X[k] = 0; C1Y[k] = 0; C2Y[k] = 0;
             uint32_t c1, c2, i1, i2;
             if (j1 < 0)       { c1 = 5; i1 = 0x5555u; }
             else if (j1 == 0) { c1 = 4; i1 = 0x5654u; }
@@ -345,84 +407,74 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             selS[k] = ((8u | c2) << 12) | (c2 << 8) | ((8u | c1) << 4) | c1;
             selI1[k] = i1; selI2[k] = i2;
         }
+        // what the left neighbour handed over for the previous odd row: diagonal of the next even row
         uint32_t hprev = HinitPk, c1prev = 0, c2prev = 0;
-        uint32_t Hout = HinitPk, Gxout = 0, c1out = 0, c2out = 0;
-        int4 nxt = make_int4((int)HinitPk, 0, 0, 0);
-        if (p > 0 && lane == 0) nxt = __ldcg(&bbuf[0]);
-        uint32_t xcur = 0, xprev = 0;
-        if (lane < n) xcur = fetch2(xs, lane);
+        uint32_t HoA = HinitPk, GoA = 0, c1oA = 0, c2oA = 0, HoB = HinitPk, GoB = 0, c1oB = 0, c2oB = 0;
+        // lane 0's left edge: rows of the previous pass's right edge, or the virtual row in pass 0
+        const int4 *feed = p > 0 ? bbuf : bbuf + vrow;
+        const int fmul = p > 0 ? 1 : 0;
+        int4 fA = __ldcg(&feed[0]), fB = __ldcg(&feed[fmul * (n > 1 ? 1 : 0)]);
+        uint32_t xw = xs[min(max(-2 * lane, 0) >> 4, x_last_word)];
 
-        const int T = n + 31;
-        for (int t = 0; t < T; ++t) {
-            const int r = t & 31;
-            if (r == 0 && t > 0) {
-                xprev = xcur;
-                const int ii = t + lane;
-                xcur = 0;
-                if (ii < n) xcur = fetch2(xs, ii);
-            }
-            const uint32_t xv = (lane <= r) ? xcur : xprev;
-            const uint32_t xi = __shfl_sync(FULL_MASK, xv, (r - lane) & 31);
-            uint32_t hin = __shfl_up_sync(FULL_MASK, Hout, 1);
-            uint32_t gin = __shfl_up_sync(FULL_MASK, Gxout, 1);
-            uint32_t c1in = __shfl_up_sync(FULL_MASK, c1out, 1);
-            uint32_t c2in = __shfl_up_sync(FULL_MASK, c2out, 1);
+        for (int t = 0; t < n_steps; ++t) {
+            const int iA = 2 * (t - lane);
+            uint32_t hinA = __shfl_up_sync(FULL_MASK, HoA, 1), ginA = __shfl_up_sync(FULL_MASK, GoA, 1);
+            uint32_t c1inA = __shfl_up_sync(FULL_MASK, c1oA, 1), c2inA = __shfl_up_sync(FULL_MASK, c2oA, 1);
+            uint32_t hinB = __shfl_up_sync(FULL_MASK, HoB, 1), ginB = __shfl_up_sync(FULL_MASK, GoB, 1);
+            uint32_t c1inB = __shfl_up_sync(FULL_MASK, c1oB, 1), c2inB = __shfl_up_sync(FULL_MASK, c2oB, 1);
             if (lane == 0) {
-                hin = (uint32_t)nxt.x; gin = (uint32_t)nxt.y; c1in = (uint32_t)nxt.z; c2in = (uint32_t)nxt.w;
-                if (p > 0 && t + 1 < n) nxt = __ldcg(&bbuf[t + 1]);
+                hinA = (uint32_t)fA.x; ginA = (uint32_t)fA.y; c1inA = (uint32_t)fA.z; c2inA = (uint32_t)fA.w;
+                hinB = (uint32_t)fB.x; ginB = (uint32_t)fB.y; c1inB = (uint32_t)fB.z; c2inB = (uint32_t)fB.w;
             }
-            const int i = t - lane;
-            if (i >= 0 && i < n) {
-                const uint32_t sh = xi * 8u;
-                const bool z = (i == 0);
-                const uint32_t Rlo = (z ? baseZ : baseN) ^ ((z ? dZ : dN) << sh);
-                const uint32_t Rhi = ((xi == y10) ? Mz : Xz) | (((xi == y20) ? Mz : Xz) << 16);
-                const uint32_t Mlo = 0x01010101u ^ (1u << sh);
-                const uint32_t Mhi = 0x00010000u | (xi != y10 ? 1u : 0u) | (xi != y20 ? 0x01000000u : 0u);
-                uint32_t Hd = hprev, Gl = gin, cd1 = c1prev, cd2 = c2prev, cl1 = c1in, cl2 = c2in;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint32_t s = prmt(Rlo, Rhi, selS[k]);
-                    const uint32_t inc1 = prmt(Mlo, Mhi, selI1[k]);
-                    const uint32_t inc2 = prmt(Mlo, Mhi, selI2[k]);
-                    const uint32_t Gu = Gy[k];
-                    const uint32_t cu1 = C1[k], cu2 = C2[k];
-                    const uint32_t h = __vadd2(__vimax3_s16x2(Hd, Gu, Gl), s);
-                    const uint32_t o = __vadd2(Hd, GOpk);
-                    const uint32_t gy = __viaddmax_s16x2(Gu, GEpk, o);
-                    const uint32_t gx = __viaddmax_s16x2(Gl, GEpk, o);
-                    bool pUhi, pUlo, pDhi, pDlo;
-                    const uint32_t g = __vibmax_s16x2(gy, gx, &pUhi, &pUlo);     // gy >= gx
-                    (void)__vibmax_s16x2(h, g, &pDhi, &pDlo);                    // h >= max(gy, gx)
-                    const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
-                    const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
-                    const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
-                    Hd = H[k]; cd1 = cu1; cd2 = cu2;
-                    H[k] = h; Gy[k] = gy; C1[k] = c1; C2[k] = c2;
-                    Gl = gx; cl1 = c1; cl2 = c2;
-                }
-                hprev = hin; c1prev = c1in; c2prev = c2in;
-                Hout = H[K - 1]; Gxout = Gl; c1out = cl1; c2out = cl2;
-                if (lane == 31) {
-                    if (p < P - 1) {
-                        __stcg(&bbuf[i], make_int4((int)Hout, (int)Gxout, (int)c1out, (int)c2out));
-                    } else {
-                        const int h1 = lo16(Hout), h2 = hi16(Hout);
-                        if (h1 > colBest1) { colBest1 = h1; colI1 = i; colC1 = c1out; }
-                        if (h2 > colBest2) { colBest2 = h2; colI2 = i; colC2 = c2out; }
+            // prefetch lane 0's next two rows (every lane issues the same address) and this lane's next x word
+            fA = __ldcg(&feed[fmul * min(2 * t + 2, n - 1)]);
+            fB = __ldcg(&feed[fmul * min(2 * t + 3, n - 1)]);
+            const uint32_t xi2 = (xw >> ((iA & 15) * 2)) & 15u;
+            xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
+            if (iA >= 0 && iA < n) {
+                const bool store = (lane == 31) && !last_pass;
+                {   // even row iA: previous row in X, result in Y
+                    const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
+                    duo_row<K>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
+                               (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
+                               hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
+                    if (store) __stcg(&bbuf[iA], make_int4((int)HoA, (int)GoA, (int)c1oA, (int)c2oA));
+                    if (last_pass) {   // last column, rows ascending, strict >; every lane tracks, lane 31 is read
+                        bool ghi, glo;                               // best >= candidate: keep
+                        colBestPk = __vibmax_s16x2(colBestPk, HoA, &ghi, &glo);
+                        if (!glo) { colI1 = iA; colC1 = c1oA; }
+                        if (!ghi) { colI2 = iA; colC2 = c2oA; }
                     }
                 }
+                if (iA + 1 < n) {   // odd row iA+1: previous row in Y, result in X
+                    const int4 T = tab[xi2 >> 2];
+                    duo_row<K>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
+                               (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
+                               hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
+                    if (store) __stcg(&bbuf[iA + 1], make_int4((int)HoB, (int)GoB, (int)c1oB, (int)c2oB));
+                    if (last_pass) {
+                        bool ghi, glo;
+                        colBestPk = __vibmax_s16x2(colBestPk, HoB, &ghi, &glo);
+                        if (!glo) { colI1 = iA + 1; colC1 = c1oB; }
+                        if (!ghi) { colI2 = iA + 1; colC2 = c2oB; }
+                    }
+                }
+                hprev = hinB; c1prev = c1inB; c2prev = c2inB;
             }
         }
         __syncwarp();
+        // last row of this pass (in Y when n is odd, in X when even): columns ascending, strict >
         int bv1 = INT_MIN, bj1 = INT_MAX, bv2 = INT_MIN, bj2 = INT_MAX;
         uint32_t bc1 = 0, bc2 = 0;
+        const bool in_y = (n & 1);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
-            const int h1 = lo16(H[k]), h2 = hi16(H[k]);
-            if (j1 >= 0 && h1 > bv1) { bv1 = h1; bj1 = j1; bc1 = C1[k]; }
-            if (j2 >= 0 && h2 > bv2) { bv2 = h2; bj2 = j2; bc2 = C2[k]; }
+            const uint32_t hk = in_y ? HY[k] : HX[k];
+            const uint32_t ck1 = in_y ? C1Y[k] : C1X[k], ck2 = in_y ? C2Y[k] : C2X[k];
+            const int h1 = lo16(hk), h2 = hi16(hk);
+            if (j1 >= 0 && h1 > bv1) { bv1 = h1; bj1 = j1; bc1 = ck1; }
+            if (j2 >= 0 && h2 > bv2) { bv2 = h2; bj2 = j2; bc2 = ck2; }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -436,9 +488,12 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
         if (bj1 != INT_MAX && bv1 > rowBest1) { rowBest1 = bv1; rowJ1 = bj1; rowC1 = bc1; }
         if (bj2 != INT_MAX && bv2 > rowBest2) { rowBest2 = bv2; rowJ2 = bj2; rowC2 = bc2; }
     }
-    colBest1 = __shfl_sync(FULL_MASK, colBest1, 31); colI1 = __shfl_sync(FULL_MASK, colI1, 31); colC1 = __shfl_sync(FULL_MASK, colC1, 31);
-    colBest2 = __shfl_sync(FULL_MASK, colBest2, 31); colI2 = __shfl_sync(FULL_MASK, colI2, 31); colC2 = __shfl_sync(FULL_MASK, colC2, 31);
+    colBestPk = __shfl_sync(FULL_MASK, colBestPk, 31);
+    colI1 = __shfl_sync(FULL_MASK, colI1, 31); colC1 = __shfl_sync(FULL_MASK, colC1, 31);
+    colI2 = __shfl_sync(FULL_MASK, colI2, 31); colC2 = __shfl_sync(FULL_MASK, colC2, 31);
     if (lane == 0) {
+        // scores stay far above -32768 (host-checked range), so the sentinel is never a real value
+        const int colBest1 = lo16(colBestPk), colBest2 = hi16(colBestPk);
         pa_pair_result o;
         if (res1) {
             if (rowBest1 > colBest1) { o.score = rowBest1; o.end_i = n - 1; o.end_j = rowJ1; o.dist = rowC1 & 0xffffu; o.len = rowC1 >> 16; }
@@ -529,10 +584,11 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
                    const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
                    pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
+    __shared__ int4 tabs[WARPS_PER_CTA][8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
-    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;     // bbuf_rows - 1 usable rows + the virtual-column row
     const uint32_t N = S.n_seq;
     const uint64_t n_items = item_hi - item_lo;
 
@@ -576,7 +632,7 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         const uint32_t *ys1 = stage_seq(S.p2 + S.off2[y1], (uint32_t)(my1 + 15) >> 4, stage[wib][1], lane);
         const uint32_t *ys2 = stage_seq(S.p2 + S.off2[y2], (uint32_t)(my2 + 15) >> 4, stage[wib][2], lane);
         __syncwarp();
-        align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf,
+        align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib],
                           use1 ? &out[q1 - first] : nullptr, use2 ? &out[q1 + 1 - first] : nullptr, lane);
     }
 }
