@@ -310,6 +310,26 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 // updated in place.  Source and destination arrays are different registers
 // (the caller ping-pongs two rows per step), so nothing has to be copied to
 // keep H(i-1,j-1) / cnt(i-1,j-1) alive for the next column.
+// max per signed half plus "a >= b" per half: the VIMNMX.S16x2 form with two predicate outputs.
+// Same PTX as CUDA's __vibmax_s16x2, but with early-clobber outputs: the toolkit's version lets the
+// result share a register with `a` when `a` dies here, and then compares the maximum with itself.
+__device__ __forceinline__ uint32_t vibmax_s16x2(const uint32_t a, const uint32_t b, bool &ge_hi, bool &ge_lo) {
+    uint32_t val, phi, plo;
+    asm("{.reg .pred pu, pv;\n\t"
+        ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+        "max.s16x2 %0, %3, %4;\n\t"
+        "mov.b32 {rs0, rs1}, %0;\n\t"
+        "mov.b32 {rs2, rs3}, %3;\n\t"
+        "setp.eq.s16 pv, rs0, rs2;\n\t"
+        "setp.eq.s16 pu, rs1, rs3;\n\t"
+        "selp.b32 %1, 1, 0, pu;\n\t"
+        "selp.b32 %2, 1, 0, pv;}"
+        : "=&r"(val), "=&r"(phi), "=&r"(plo) : "r"(a), "r"(b));
+    ge_hi = (phi != 0);
+    ge_lo = (plo != 0);
+    return val;
+}
+
 template <int K>
 __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
                                         const uint32_t (&C1s)[K], uint32_t (&C1d)[K],
@@ -332,8 +352,8 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
         const uint32_t gy = __viaddmax_s16x2(Gu, GEpk, o);
         const uint32_t gx = __viaddmax_s16x2(Gl, GEpk, o);
         bool pUhi, pUlo, pDhi, pDlo;
-        const uint32_t g = __vibmax_s16x2(gy, gx, &pUhi, &pUlo);     // gy >= gx
-        (void)__vibmax_s16x2(h, g, &pDhi, &pDlo);                    // h >= max(gy, gx)
+        const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);         // gy >= gx
+        (void)vibmax_s16x2(h, g, pDhi, pDlo);                        // h >= max(gy, gx)
         const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
         const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
         const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
@@ -441,7 +461,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     if (store) __stcg(&bbuf[iA], make_int4((int)HoA, (int)GoA, (int)c1oA, (int)c2oA));
                     if (last_pass) {   // last column, rows ascending, strict >; every lane tracks, lane 31 is read
                         bool ghi, glo;                               // best >= candidate: keep
-                        colBestPk = __vibmax_s16x2(colBestPk, HoA, &ghi, &glo);
+                        colBestPk = vibmax_s16x2(colBestPk, HoA, ghi, glo);
                         if (!glo) { colI1 = iA; colC1 = c1oA; }
                         if (!ghi) { colI2 = iA; colC2 = c2oA; }
                     }
@@ -454,7 +474,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     if (store) __stcg(&bbuf[iA + 1], make_int4((int)HoB, (int)GoB, (int)c1oB, (int)c2oB));
                     if (last_pass) {
                         bool ghi, glo;
-                        colBestPk = __vibmax_s16x2(colBestPk, HoB, &ghi, &glo);
+                        colBestPk = vibmax_s16x2(colBestPk, HoB, ghi, glo);
                         if (!glo) { colI1 = iA + 1; colC1 = c1oB; }
                         if (!ghi) { colI2 = iA + 1; colC2 = c2oB; }
                     }
