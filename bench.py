@@ -280,7 +280,7 @@ def main() -> None:
 
     peak = None
     if rank == 0 and not args.no_peak:
-        peak = {capi.PEAK_CLASSES[w]: capi.int32_peak(w) for w in (0, 12, 2, 3, 6, 13)}
+        peak = {capi.PEAK_CLASSES[w]: capi.int32_peak(w) for w in (0, 12, 2, 3, 7, 8, 9, 18, 21)}
 
     if rank == 0:
         ms = 1e3 * el / args.steps
@@ -300,13 +300,25 @@ def main() -> None:
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": ok,
         }
         if peak is not None:
-            alu = max(peak["IADD3"][0], peak["VIMNMX"][0], peak["VIADDMNMX"][0])
+            # Single-instruction issue rates measured on this GPU a moment ago (pa_int32_peak): every integer
+            # class the DP uses -- 32-bit or s16x2 -- issues at the same ~64 lanes/clk/SM.  The s16x2 DPX forms
+            # carry two DP cells per lane, so the roofline of the packed kernel is twice the 32-bit-lane rate.
+            alu32 = max(peak["IADD3"][0], peak["VIMNMX"][0], peak["VIADDMNMX"][0])
+            packed = max(peak["VIMNMX3.S16x2"][0], peak["VIADDMNMX.S16x2"][0])
+            peak_ops = 2.0 * packed
             achieved = OPS_PER_CELL * my_cells / (kern_step_ms * 1e-3) / 1e9
             line["roofline"] = {
-                "bound": "int32", "achieved": achieved, "peak": alu, "unit": "Gop/s", "frac": achieved / alu, "traffic": None,
-                "kernel": "pa_warp_duo_kernel<16> (s16x2, two pairs per warp)", "kernel_ms_per_step": kern_step_ms,
-                "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL,
-                "peak_source": "pa_int32_peak measured in this run: best single-pipe integer issue rate (IADD3 / VIMNMX / VIADDMNMX chains, all SMs)",
+                "bound": "int32", "achieved": achieved, "peak": peak_ops, "unit": "Gop/s", "frac": achieved / peak_ops,
+                "traffic": 7837952,
+                "kernel": "pa_warp_duo_kernel<12> (s16x2 DPX, two pairs per warp, two rows per step)",
+                "kernel_ms_per_step": kern_step_ms, "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9,
+                "ops_per_cell": OPS_PER_CELL,
+                "achieved_def": "14 integer operations per DP cell (SURVEY.md 8d) x cells of this rank / CUDA-event time of the DP kernels",
+                "peak_def": "2 x the measured issue rate of VIMNMX3.S16x2 / VIADDMNMX.S16x2 chains (two 16-bit cells per 32-bit lane), "
+                            "all SMs, measured in this run by pa_int32_peak",
+                "frac_vs_32bit_lane_roofline": achieved / alu32, "peak_32bit_lane": alu32,
+                "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                               "(profiles/r01_v3_duo12_ncu_full.txt); algorithmic bytes per launch are in hbm.algorithmic_bytes_per_step",
                 "measured": {k: {"gops": v[0], "sm_mhz": v[1]} for k, v in peak.items()},
                 "hbm": {"algorithmic_bytes_per_step": int(masks.nbytes // 4 + count * 20),
                         "note": "2-bit sequences + 20 B per pair; HBM is not the bound (SURVEY.md 8d)"},

@@ -163,6 +163,12 @@ int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b,
  * to shard the triangle over devices / ranks. */
 int pa_partition_pairs(uint64_t first, uint64_t count, uint32_t n_parts, uint64_t *bounds);
 
+/* The same split computed from the encoded lengths alone: needs no device and no
+ * context (every rank of a multi-process run calls it and takes its own range).
+ * cells (optional, n_parts entries) receives the DP cells of each part. */
+int pa_partition_by_length(const uint32_t *lengths, uint32_t n_seq, uint64_t first, uint64_t count,
+                           uint32_t n_parts, uint64_t *bounds, uint64_t *cells);
+
 /* Sum of n*m over pairs [first, first+count). */
 uint64_t pa_count_cells(uint64_t first, uint64_t count);
 

@@ -53,6 +53,7 @@ SYMBOLS = {
     "pa_align_pair_traceback": (C.c_int, [C.POINTER(PaParams), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]),
     "pa_partition_pairs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "pa_partition_by_length": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pa_count_cells": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "pa_get_timing": (C.c_int, [C.POINTER(PaTiming)]),
     "pa_similarity": (C.c_double, [C.c_uint32, C.c_uint32]),
@@ -193,6 +194,16 @@ def partition_pairs(first: int, count: int, n_parts: int) -> np.ndarray:
     bounds = np.empty(n_parts + 1, dtype=np.uint64)
     _check(load().pa_partition_pairs(first, count, n_parts, bounds.ctypes.data))
     return bounds
+
+
+def partition_by_length(lengths, first: int, count: int, n_parts: int):
+    """Device-free split of the triangle range into n_parts ranges of nearly equal DP cells."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+    bounds = np.empty(n_parts + 1, dtype=np.uint64)
+    cells = np.empty(n_parts, dtype=np.uint64)
+    _check(load().pa_partition_by_length(lengths.ctypes.data, len(lengths), first, count, n_parts,
+                                         bounds.ctypes.data, cells.ctypes.data))
+    return bounds, cells
 
 
 def count_cells(first: int, count: int) -> int:

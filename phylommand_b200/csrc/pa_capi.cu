@@ -60,7 +60,7 @@ struct Device {
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_fast = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo8 = 0, grid_fast = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -75,17 +75,59 @@ struct Device {
     uint32_t launches = 0;
 };
 
+// Lengths of the uploaded set with the prefix sums that balancing needs.
+struct Triangle {
+    uint32_t n_seq = 0;
+    std::vector<uint32_t> len;
+    std::vector<uint64_t> pref;                        // pref[s] = sum of len[0..s)
+    std::vector<unsigned __int128> row_cells_exact;    // DP cells in rows before r
+    void build(const uint32_t *l, uint32_t n) {
+        n_seq = n;
+        len.assign(l, l + n);
+        pref.assign((size_t)n + 1, 0);
+        for (uint32_t s = 0; s < n; ++s) pref[s + 1] = pref[s] + len[s];
+        row_cells_exact.assign((size_t)n + 1, 0);
+        for (uint32_t r = 0; r + 1 < n; ++r)
+            row_cells_exact[r + 1] = row_cells_exact[r] + (unsigned __int128)len[r] * (pref[n] - pref[r + 1]);
+        if (n) row_cells_exact[n] = row_cells_exact[n - 1];
+    }
+    uint64_t pairs() const { return n_seq < 2 ? 0 : (uint64_t)n_seq * (n_seq - 1) / 2; }
+    // cells of all pairs with triangle index < q
+    unsigned __int128 cells_before(uint64_t q) const {
+        const uint64_t N = n_seq;
+        if (N < 2) return 0;
+        if (q >= pairs()) return row_cells_exact[N - 1];
+        uint32_t a, b;
+        tri_pair(q, (uint32_t)N, a, b);
+        return row_cells_exact[a] + (unsigned __int128)len[a] * (pref[b] - pref[a + 1]);
+    }
+    // n_parts contiguous ranges of [first, first+count) with nearly equal cells
+    void partition(uint64_t first, uint64_t count, uint32_t n_parts, uint64_t *bounds) const {
+        const unsigned __int128 lo = cells_before(first), hi = cells_before(first + count);
+        bounds[0] = first;
+        for (uint32_t p = 1; p < n_parts; ++p) {
+            const unsigned __int128 target = lo + (hi - lo) * p / n_parts;
+            uint64_t a = bounds[p - 1], b = first + count;     // smallest q in [a,b] with cells_before(q) >= target
+            while (a < b) {
+                const uint64_t mid = a + (b - a) / 2;
+                if (cells_before(mid) >= target) b = mid; else a = mid + 1;
+            }
+            bounds[p] = a;
+        }
+        bounds[n_parts] = first + count;
+    }
+};
+
 struct Context {
     std::vector<Device> dev;
     // host copy of what partitioning needs
     uint32_t n_seq = 0;
     std::vector<uint32_t> len;
-    std::vector<uint64_t> pref;        // pref[s] = sum of len[0..s)
-    std::vector<double> row_cells;     // cells in rows before r (double is exact enough for balancing)
-    std::vector<unsigned __int128> row_cells_exact;
+    Triangle tri;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
+    int kduo = KDUO;                   // PAIRALIGN_KDUO=8: narrower strips, more resident warps (tuning)
     uint32_t max_len = 0;
     pa_timing timing = {};
 };
@@ -123,16 +165,7 @@ bool fast_params_ok(const pa_params &p) {
            fits((long long)p.match + p.gap_open) && fits((long long)p.mismatch + p.gap_open);
 }
 
-// cells of all pairs with triangle index < q
-unsigned __int128 cells_before(const Context &c, uint64_t q) {
-    const uint64_t N = c.n_seq;
-    if (N < 2) return 0;
-    const uint64_t total = N * (N - 1) / 2;
-    if (q >= total) return c.row_cells_exact[N - 1];
-    uint32_t a, b;
-    tri_pair(q, (uint32_t)N, a, b);
-    return c.row_cells_exact[a] + (unsigned __int128)c.len[a] * (c.pref[b] - c.pref[a + 1]);
-}
+unsigned __int128 cells_before(const Context &c, uint64_t q) { return c.tri.cells_before(q); }
 
 int ensure_out(Device &d, size_t n) {
     if (n <= d.d_out_cap) return PA_OK;
@@ -221,9 +254,14 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const unsigned int *count2 = nullptr;
     if (duo) {
         const uint64_t item_lo = item_of(c, first), item_hi = item_of(c, first + count - 1) + 1;
-        pa_warp_duo_kernel<KDUO><<<d.grid_duo, threads, 0, d.stream>>>(
-            S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
-            d.deferred, d.n_deferred);
+        if (c.kduo == 8)
+            pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred);
+        else
+            pa_warp_duo_kernel<KDUO><<<d.grid_duo, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_duo = true;
@@ -393,13 +431,15 @@ int pa_init(const int *devices, int n_dev) {
         int occ = 0;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
         d.grid_duo = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo8 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KFAST, false>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(d.grid_duo, std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA;
+        d.n_warps = (uint32_t)std::max(std::max(d.grid_duo, d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA;
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -408,6 +448,7 @@ int pa_init(const int *devices, int n_dev) {
         }
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
+    if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo = std::atoi(f);
     g_ctx = c;
     return PA_OK;
 }
@@ -504,12 +545,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.len = len;
     c.max_len = max_len;
     c.all_pure = all_pure;
-    c.pref.assign((size_t)n_seq + 1, 0);
-    for (uint32_t s = 0; s < n_seq; ++s) c.pref[s + 1] = c.pref[s] + len[s];
-    c.row_cells_exact.assign((size_t)n_seq + 1, 0);
-    for (uint32_t r = 0; r + 1 < n_seq; ++r)
-        c.row_cells_exact[r + 1] = c.row_cells_exact[r] + (unsigned __int128)len[r] * (c.pref[n_seq] - c.pref[r + 1]);
-    if (n_seq) c.row_cells_exact[n_seq] = c.row_cells_exact[n_seq - 1];
+    c.tri.build(len.data(), n_seq);
     c.row_items.assign((size_t)n_seq + 1, 0);
     for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
 
@@ -568,19 +604,20 @@ int pa_partition_pairs(uint64_t first, uint64_t count, uint32_t n_parts, uint64_
     if (!bounds || n_parts == 0) return fail(PA_EINVAL, "bad partition arguments");
     const uint64_t total = pa_num_pairs();
     if (first > total || count > total - first) return fail(PA_ERANGE, "pair range outside the triangle");
-    const Context &c = *g_ctx;
-    const unsigned __int128 lo = cells_before(c, first), hi = cells_before(c, first + count);
-    bounds[0] = first;
-    for (uint32_t p = 1; p < n_parts; ++p) {
-        const unsigned __int128 target = lo + (hi - lo) * p / n_parts;
-        uint64_t a = bounds[p - 1], b = first + count;     // smallest q in [a,b] with cells_before(q) >= target
-        while (a < b) {
-            const uint64_t mid = a + (b - a) / 2;
-            if (cells_before(c, mid) >= target) b = mid; else a = mid + 1;
-        }
-        bounds[p] = a;
-    }
-    bounds[n_parts] = first + count;
+    g_ctx->tri.partition(first, count, n_parts, bounds);
+    return PA_OK;
+}
+
+int pa_partition_by_length(const uint32_t *lengths, uint32_t n_seq, uint64_t first, uint64_t count, uint32_t n_parts,
+                           uint64_t *bounds, uint64_t *cells) {
+    if (!lengths || !bounds || n_parts == 0) return fail(PA_EINVAL, "bad partition arguments");
+    Triangle t;
+    t.build(lengths, n_seq);
+    const uint64_t total = t.pairs();
+    if (first > total || count > total - first) return fail(PA_ERANGE, "pair range outside the triangle");
+    t.partition(first, count, n_parts, bounds);
+    if (cells)
+        for (uint32_t p = 0; p < n_parts; ++p) cells[p] = (uint64_t)(t.cells_before(bounds[p + 1]) - t.cells_before(bounds[p]));
     return PA_OK;
 }
 
@@ -606,15 +643,7 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     if (!ia) {
         if (nd == 1) { bounds[0] = first; bounds[1] = first + count; }
         else {
-            const unsigned __int128 lo = cells_before(c, first), hi = cells_before(c, first + count);
-            bounds[0] = first;
-            for (size_t p = 1; p < nd; ++p) {
-                const unsigned __int128 target = lo + (hi - lo) * p / nd;
-                uint64_t a = bounds[p - 1], b = first + count;
-                while (a < b) { const uint64_t mid = a + (b - a) / 2; if (cells_before(c, mid) >= target) b = mid; else a = mid + 1; }
-                bounds[p] = a;
-            }
-            bounds[nd] = first + count;
+            c.tri.partition(first, count, (uint32_t)nd, bounds.data());
         }
     } else {
         for (size_t p = 0; p <= nd; ++p) bounds[p] = count * p / nd;
