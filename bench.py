@@ -234,10 +234,20 @@ def main() -> None:
         capi.align_all_pairs_device(d_out.data_ptr(), first, count)
         return capi.timing()
 
+    e2e_parts = {"upload_ms": 0.0, "align_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "calls": 0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         capi.upload_packed(masks, offsets)
+        t1 = time.perf_counter()
         capi.align_all_pairs(first, count, h_out)
-        return capi.timing()
+        t = capi.timing()
+        e2e_parts["upload_ms"] += 1e3 * (t1 - t0)
+        e2e_parts["align_ms"] += t["total_ms"]
+        e2e_parts["kernel_ms"] += t["kernel_ms"]
+        e2e_parts["d2h_ms"] += t["d2h_ms"]
+        e2e_parts["calls"] += 1
+        return t
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -296,7 +306,9 @@ def main() -> None:
                        "l2": "256 MiB device write between steps, outside the timed region; the kernel is ALU-bound"},
             "e2e": {"value": total_pairs / (el_e2e / args.steps), "unit": "pairs/s", "h2d_bytes_per_step": int(masks.nbytes + offsets.nbytes),
                     "d2h_bytes_per_step": int(count * capi.RESULT_DTYPE.itemsize), "ms_per_step": 1e3 * el_e2e / args.steps,
-                    "gcups": total_cells / (el_e2e / args.steps) / 1e9},
+                    "gcups": total_cells / (el_e2e / args.steps) / 1e9,
+                    "rank0_breakdown_ms_per_call": {k: v / max(1, e2e_parts["calls"]) for k, v in e2e_parts.items() if k != "calls"},
+                    "path": "pa_upload_sequences(host masks) + pa_align_all_pairs(host records): pack, H2D, kernels, D2H, copy-out"},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": ok,
         }
         if peak is not None:

@@ -57,6 +57,7 @@ struct Device {
     uint32_t *deferred = nullptr, *deferred2 = nullptr;
     size_t deferred_cap = 0;
     unsigned long long *row_items = nullptr;  // items (pairs of pairs) in rows before a; n_seq+1 entries
+    size_t cap_row_items = 0, cap_p2 = 0, cap_p4 = 0, cap_off2 = 0, cap_off4 = 0, cap_len = 0, cap_pure = 0, cap_bbuf = 0;
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
@@ -551,27 +552,38 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
 
     for (auto &d : c.dev) {
         CU(cudaSetDevice(d.id));
-        cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure); cudaFree(d.bbuf);
-        cudaFree(d.row_items);
-        d.p2 = d.p4 = d.off2 = d.off4 = d.len = nullptr; d.pure = nullptr; d.bbuf = nullptr; d.row_items = nullptr;
-        CU(cudaMalloc(&d.row_items, c.row_items.size() * sizeof(unsigned long long)));
-        CU(cudaMemcpy(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&d.p2, p2.size() * 4));
-        CU(cudaMalloc(&d.p4, p4.size() * 4));
-        CU(cudaMalloc(&d.off2, std::max<size_t>(n_seq, 1) * 4));
-        CU(cudaMalloc(&d.off4, std::max<size_t>(n_seq, 1) * 4));
-        CU(cudaMalloc(&d.len, std::max<size_t>(n_seq, 1) * 4));
-        CU(cudaMalloc(&d.pure, std::max<size_t>(n_seq, 1)));
-        CU(cudaMemcpy(d.p2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(d.p4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice));
-        if (n_seq) {
-            CU(cudaMemcpy(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice));
-        }
+        // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
+        auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
+            if (bytes <= cap && *ptr) return cudaSuccess;
+            cudaFree(*ptr);
+            *ptr = nullptr; cap = 0;
+            cudaError_t e = cudaMalloc(ptr, bytes);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        };
+        const size_t nidx = std::max<size_t>(n_seq, 1);
+        CU(grow((void **)&d.row_items, d.cap_row_items, c.row_items.size() * sizeof(unsigned long long)));
+        CU(grow((void **)&d.p2, d.cap_p2, p2.size() * 4));
+        CU(grow((void **)&d.p4, d.cap_p4, p4.size() * 4));
+        CU(grow((void **)&d.off2, d.cap_off2, nidx * 4));
+        CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
+        CU(grow((void **)&d.len, d.cap_len, nidx * 4));
+        CU(grow((void **)&d.pure, d.cap_pure, nidx));
         d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
-        CU(cudaMalloc(&d.bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
+        CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
+        CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.p2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.p4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice, d.stream));
+        if (n_seq) {
+            CU(cudaMemcpyAsync(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
+        }
+    }
+    for (auto &d : c.dev) {       // the host vectors above die at return
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.stream));
     }
     return PA_OK;
 }
