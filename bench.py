@@ -260,7 +260,7 @@ def main() -> None:
             t = fn()
             torch.cuda.synchronize()
             el += time.perf_counter() - t0
-            kern += t["dp_duo_ms"] + t["dp_fast_ms"] + t["dp_general_ms"]
+            kern += t["dp_duo_ms"] + t["dp_fast_ms"] + t["dp_cta_ms"] + t["dp_general_ms"]
             launches += t["kernel_launches"]
         barrier()
         v = torch.tensor([el, kern], dtype=torch.float64, device="cuda")

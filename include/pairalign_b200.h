@@ -82,6 +82,7 @@ typedef struct {
     double   dp_fast_ms;     /* the 32-bit 2-bit register-wavefront kernel (one pair per warp) */
     double   dp_general_ms;  /* the IUPAC/gap (int32 wrap) kernel alone                    */
     double   dp_duo_ms;      /* the s16x2 kernel (two pairs per warp); with -A: the stats kernel */
+    double   dp_cta_ms;      /* the CTA-per-pair kernel for long pairs                       */
 } pa_timing;
 
 /* ---- life cycle --------------------------------------------------------- */

@@ -2,6 +2,7 @@
 // store, launch logic and result transfer.  No CPU fallback exists here: every
 // compute entry point needs a CUDA device.
 #include "pa_dp.cuh"
+#include "pa_dp32.cuh"
 #include "pa_peak.cuh"
 
 #include <algorithm>
@@ -21,7 +22,8 @@ namespace {
 using namespace pa;
 
 constexpr int KDUO = 12;      // columns per lane, s16x2 two-pairs-per-warp path
-constexpr int KFAST = 16;     // columns per lane, 32-bit 2-bit path
+constexpr int KFAST = 16;     // columns per lane, int32 2-bit path (warp kernel and CTA kernel)
+constexpr uint32_t LONG_LEN = 8192;   // longer A/C/G/T pairs take a whole CTA (pa_cta32_kernel)
 constexpr int KGEN = 8;       // columns per lane, IUPAC/gap path
 constexpr uint64_t CHUNK_PAIRS = 1ull << 22;   // pairs per launch (84 MB of records)
 
@@ -53,15 +55,15 @@ struct Device {
     uint8_t *pure = nullptr;
     // scratch
     unsigned long long *counters = nullptr;   // [0] fast work counter, [1] general work counter
-    unsigned int *n_deferred = nullptr;       // [0] deferred by the s16x2 kernel, [1] deferred by the 32-bit kernel
-    uint32_t *deferred = nullptr, *deferred2 = nullptr;
+    unsigned int *n_deferred = nullptr;       // [0] deferred by the s16x2 kernel, [1] non-A/C/G/T, [2] long pairs
+    uint32_t *deferred = nullptr, *deferred2 = nullptr, *deferred3 = nullptr;
     size_t deferred_cap = 0;
     unsigned long long *row_items = nullptr;  // items (pairs of pairs) in rows before a; n_seq+1 entries
     size_t cap_row_items = 0, cap_p2 = 0, cap_p4 = 0, cap_off2 = 0, cap_off4 = 0, cap_len = 0, cap_pure = 0, cap_bbuf = 0;
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo8 = 0, grid_fast = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo8 = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -71,6 +73,9 @@ struct Device {
     cudaEvent_t ev_done[2] = {};
     bool chunk_duo = false, chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
     cudaEvent_t ev_mid = nullptr;                 // between the s16x2 kernel and the 32-bit follow-up
+    cudaEvent_t ev_cta = nullptr;                 // after the CTA-per-pair kernel
+    bool chunk_cta = false;
+    double cta_ms = 0;
     // timing accumulators of the last call
     double duo_ms = 0, fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
     uint32_t launches = 0;
@@ -128,7 +133,9 @@ struct Context {
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
-    int kduo = KDUO;                   // PAIRALIGN_KDUO=8: narrower strips, more resident warps (tuning)
+    int kduo = KDUO;                   // strip width of the s16x2 kernel: 12 or 8, whichever pads the uploaded lengths less
+    int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 overrides the choice (tuning)
+    bool no_cta = false;               // PAIRALIGN_NO_CTA=1: long pairs stay on the one-pair-per-warp kernel (comparison)
     uint32_t max_len = 0;
     pa_timing timing = {};
 };
@@ -140,9 +147,10 @@ void free_device(Device &d) {
     if (d.id < 0) return;
     cudaSetDevice(d.id);
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
-    cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.bbuf);
+    cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3); cudaFree(d.bbuf);
     cudaFree(d.row_items);
     if (d.ev_mid) cudaEventDestroy(d.ev_mid);
+    if (d.ev_cta) cudaEventDestroy(d.ev_cta);
     for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
     cudaFree(d.d_ia); cudaFree(d.d_ib);
     for (auto &e : d.ev) if (e) cudaEventDestroy(e);
@@ -186,10 +194,11 @@ int ensure_out(Device &d, size_t n) {
 
 int ensure_deferred(Device &d, size_t n) {
     if (n <= d.deferred_cap) return PA_OK;
-    cudaFree(d.deferred); cudaFree(d.deferred2);
-    d.deferred = d.deferred2 = nullptr; d.deferred_cap = 0;
+    cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3);
+    d.deferred = d.deferred2 = d.deferred3 = nullptr; d.deferred_cap = 0;
     CU(cudaMalloc(&d.deferred, n * sizeof(uint32_t)));
     CU(cudaMalloc(&d.deferred2, n * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.deferred3, n * sizeof(uint32_t)));
     d.deferred_cap = n;
     return PA_OK;
 }
@@ -228,9 +237,9 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const SeqStore S = store_of(d, c.n_seq);
     Scoring sc{p.match, p.mismatch, p.gap_open, p.gap_ext};
     PairSource src{first, d_ia, d_ib, nullptr};
-    CU(cudaMemsetAsync(d.counters, 0, 3 * sizeof(unsigned long long), d.stream));
-    CU(cudaMemsetAsync(d.n_deferred, 0, 2 * sizeof(unsigned int), d.stream));
-    d.chunk_duo = d.chunk_fast = d.chunk_gen = false;
+    CU(cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.n_deferred, 0, 3 * sizeof(unsigned int), d.stream));
+    d.chunk_duo = d.chunk_fast = d.chunk_cta = d.chunk_gen = false;
     const int threads = WARPS_PER_CTA * 32;
     if (p.aligned) {
         d.chunk_duo = true;
@@ -239,6 +248,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         CU(cudaGetLastError());
         CU(cudaEventRecord(d.ev[1], d.stream));
         CU(cudaEventRecord(d.ev_mid, d.stream));
+        CU(cudaEventRecord(d.ev_cta, d.stream));
         CU(cudaEventRecord(d.ev[2], d.stream));
         CU(cudaEventRecord(d.ev[3], d.stream));
         d.launches += 1;
@@ -250,7 +260,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;
     CU(cudaEventRecord(d.ev[0], d.stream));
-    bool stage2 = false, stage3 = false;
+    bool stage2 = false, stage_cta = false, stage_gen = false;
     PairSource src2 = src;
     const unsigned int *count2 = nullptr;
     if (duo) {
@@ -274,14 +284,27 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     }
     CU(cudaEventRecord(d.ev[1], d.stream));
     if (stage2) {
-        pa_warp_dp_kernel<KFAST, false><<<d.grid_fast, threads, 0, d.stream>>>(
-            S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1);
+        const bool route_long = c.max_len > LONG_LEN && !c.no_cta;
+        pa_warp32_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(
+            S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1,
+            route_long ? d.deferred3 : nullptr, d.n_deferred + 2, LONG_LEN);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_fast = true;
-        stage3 = !c.all_pure;
+        stage_cta = route_long;
+        stage_gen = !c.all_pure;
     }
     CU(cudaEventRecord(d.ev_mid, d.stream));
+    if (stage_cta) {
+        PairSource src3 = src;
+        src3.idx = d.deferred3;
+        pa_cta32_kernel<KFAST><<<d.grid_cta, CTA_WARPS * 32, 0, d.stream>>>(
+            S, sc, src3, d.n_deferred + 2, d.counters + 3, d.bbuf, d.bbuf_rows, d_out);
+        CU(cudaGetLastError());
+        d.launches += 1;
+        d.chunk_cta = true;
+    }
+    CU(cudaEventRecord(d.ev_cta, d.stream));
     CU(cudaEventRecord(d.ev[2], d.stream));
     if (!fast) {
         pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, threads, 0, d.stream>>>(
@@ -289,11 +312,11 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_gen = true;
-    } else if (stage3) {
-        PairSource src3 = src;
-        src3.idx = d.deferred2;
+    } else if (stage_gen) {
+        PairSource src4 = src;
+        src4.idx = d.deferred2;
         pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, threads, 0, d.stream>>>(
-            S, sc, src3, count, d.n_deferred + 1, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
+            S, sc, src4, count, d.n_deferred + 1, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_gen = true;
@@ -308,6 +331,8 @@ int collect_chunk_times(Device &d) {
     if (d.chunk_duo) d.duo_ms += ms;
     CU(cudaEventElapsedTime(&ms, d.ev[1], d.ev_mid));
     if (d.chunk_fast) d.fast_ms += ms;
+    CU(cudaEventElapsedTime(&ms, d.ev_mid, d.ev_cta));
+    if (d.chunk_cta) d.cta_ms += ms;
     CU(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]));
     if (d.chunk_gen) d.gen_ms += ms;
     return PA_OK;
@@ -320,7 +345,7 @@ int collect_chunk_times(Device &d) {
 int run_range(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
               const uint32_t *h_ia, const uint32_t *h_ib, pa_pair_result *out, pa_pair_result *d_resident) {
     CU(cudaSetDevice(d.id));
-    d.duo_ms = d.fast_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
+    d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
     d.launches = 0;
     if (count == 0) return PA_OK;
     const uint64_t chunk = std::min<uint64_t>(CHUNK_PAIRS, count);
@@ -427,20 +452,23 @@ int pa_init(const int *devices, int n_dev) {
         for (auto &ev : d.ev) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
         for (auto &ev : d.ev_done) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
         if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_mid);
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 3 * sizeof(unsigned long long));
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 2 * sizeof(unsigned int));
+        if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_cta);
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 4 * sizeof(unsigned long long));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
         int occ = 0;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
         d.grid_duo = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
         d.grid_duo8 = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KFAST, false>, WARPS_PER_CTA * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
+        d.grid_cta = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(d.grid_duo, d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA;
+        d.n_warps = (uint32_t)std::max(std::max(std::max(d.grid_duo, d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -449,7 +477,8 @@ int pa_init(const int *devices, int n_dev) {
         }
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
-    if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo = std::atoi(f);
+    if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
+    if (const char *f = std::getenv("PAIRALIGN_NO_CTA")) c->no_cta = (f[0] == '1');
     g_ctx = c;
     return PA_OK;
 }
@@ -547,6 +576,15 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.max_len = max_len;
     c.all_pure = all_pure;
     c.tri.build(len.data(), n_seq);
+    {   // column slots are handed out in passes of 32*K: pick the strip width that wastes fewer pad columns
+        uint64_t slots8 = 0, slots12 = 0;
+        for (uint32_t s = 0; s < n_seq; ++s) {
+            slots8 += ((uint64_t)len[s] + 255) / 256 * 256;
+            slots12 += ((uint64_t)len[s] + 383) / 384 * 384;
+        }
+        c.kduo = (slots8 * 100 < slots12 * 97) ? 8 : KDUO;      // K=12 amortises the per-step work better: prefer it unless 8 saves > 3 %
+        if (c.kduo_forced == 8 || c.kduo_forced == 12) c.kduo = c.kduo_forced;
+    }
     c.row_items.assign((size_t)n_seq + 1, 0);
     for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
 
@@ -680,7 +718,8 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
         const Device &d = c.dev[p];
-        tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.gen_ms);
+        tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.cta_ms + d.gen_ms);
+        tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
         tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);
         tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
         tm.dp_general_ms = std::max(tm.dp_general_ms, d.gen_ms);

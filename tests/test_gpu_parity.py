@@ -232,3 +232,37 @@ def test_s16x2_kernel_near_its_int16_limit(gpu, oracle):
     assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] > 0
     _same(got, _oracle_all(oracle, enc))
     assert int(got[2]["score"]) == 7 * len(enc[0])  # pair (0, 3)
+
+
+def test_cta_per_pair_kernel_long_pairs(gpu, oracle):
+    """Pairs longer than 8192 take a whole CTA: 8 warps on consecutive 512-column blocks of one pair,
+    edges through shared-memory rings (and global memory for the wrap-around).  18-24 blocks = 3 rounds."""
+    _, seqs = synth.make_long(3, 501, length=10500, spread=0.12)
+    enc = [synth.to_masks(s) for s in seqs]
+    enc.append(enc[1][:300].copy())                  # long x against a one-block y (and the other way round)
+    enc.append(enc[0][:8193].copy())                 # just above the threshold, odd length
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_cta_ms"] > 0
+    _same(got, _oracle_all(oracle, enc, threads=10))
+    # explicit list, both orientations
+    ia, ib = np.array([3, 0, 4, 2]), np.array([0, 3, 2, 4])
+    rev = gpu.align_pairs(ia, ib)
+    for k in range(len(ia)):
+        assert tuple(rev[k]) == tuple(oracle.align_forward(enc[ia[k]], enc[ib[k]])), (ia[k], ib[k])
+
+
+def test_all_four_dp_kernels_in_one_call(gpu, oracle):
+    """s16x2 (short), int32 warp (4.6-8 kb), CTA (> 8 kb) and general (IUPAC) pairs from one upload."""
+    _, short = synth.make_random(6, 601, 200, 900)
+    _, mid = synth.make_long(2, 602, length=6000, spread=0.1)
+    _, long_ = synth.make_long(2, 603, length=9000, spread=0.05)
+    _, amb = synth.make_random(3, 604, 300, 700, iupac=0.02)
+    enc = [synth.to_masks(s) for s in short + mid + long_] + [gpu.encode("N" + synth.to_text(s)) for s in amb]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] > 0 and t["dp_cta_ms"] > 0 and t["dp_general_ms"] > 0
+    assert t["kernel_launches"] == 4
+    _same(got, _oracle_all(oracle, enc, threads=10))
