@@ -63,7 +63,7 @@ struct Device {
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo8 = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -133,8 +133,11 @@ struct Context {
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
-    int kduo = KDUO;                   // strip width of the s16x2 kernel: 12 or 8, whichever pads the uploaded lengths less
+    int kduo = KDUO;                   // strip width of the s16x2 kernel
     int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 overrides the choice (tuning)
+    int duo_minb = 1;                  // PAIRALIGN_DUO_MINB=3: register-capped build of the s16x2 kernel, 3 CTAs per SM (tuning)
+    bool force_cta = false;            // PAIRALIGN_FORCE_CTA=1: every long pair takes a CTA regardless of how many there are
+    uint64_t est_long_pairs = 0;       // pairs of the whole triangle with a sequence longer than LONG_LEN
     bool no_cta = false;               // PAIRALIGN_NO_CTA=1: long pairs stay on the one-pair-per-warp kernel (comparison)
     uint32_t max_len = 0;
     pa_timing timing = {};
@@ -269,6 +272,10 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred);
+        else if (c.duo_minb == 3)
+            pa_warp_duo_kernel<KDUO, 3><<<d.grid_duo3, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred);
         else
             pa_warp_duo_kernel<KDUO><<<d.grid_duo, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
@@ -284,7 +291,10 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     }
     CU(cudaEventRecord(d.ev[1], d.stream));
     if (stage2) {
-        const bool route_long = c.max_len > LONG_LEN && !c.no_cta;
+        // a CTA per pair pays off when there are too few long pairs to keep every warp of the one-pair-per-warp
+        // kernel busy; with thousands of them that kernel is the faster one (no hand-over, no block-count rounding)
+        const bool route_long = c.max_len > LONG_LEN && !c.no_cta &&
+                                (c.force_cta || c.est_long_pairs < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
         pa_warp32_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(
             S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1,
             route_long ? d.deferred3 : nullptr, d.n_deferred + 2, LONG_LEN);
@@ -458,6 +468,8 @@ int pa_init(const int *devices, int n_dev) {
         int occ = 0;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
         d.grid_duo = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO, 3>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo3 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
         d.grid_duo8 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
@@ -468,7 +480,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(d.grid_duo, d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -479,6 +491,8 @@ int pa_init(const int *devices, int n_dev) {
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_NO_CTA")) c->no_cta = (f[0] == '1');
+    if (const char *f = std::getenv("PAIRALIGN_DUO_MINB")) c->duo_minb = std::atoi(f);
+    if (const char *f = std::getenv("PAIRALIGN_FORCE_CTA")) c->force_cta = (f[0] == '1');
     g_ctx = c;
     return PA_OK;
 }
@@ -576,6 +590,19 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.max_len = max_len;
     c.all_pure = all_pure;
     c.tri.build(len.data(), n_seq);
+    {
+        uint64_t n_long = 0;
+        for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
+        c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
+    }
+    // strip width of the s16x2 kernel: 12 measured faster than 8 on both the 1.5 kb and the 400-900 bp sets
+    // (fewer pad columns with 8 do not make up for its higher per-step overhead)
+    c.kduo = (c.kduo_forced == 8 || c.kduo_forced == 12) ? c.kduo_forced : KDUO;
+    {
+        uint64_t n_long = 0;
+        for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
+        c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
+    }
     {   // column slots are handed out in passes of 32*K: pick the strip width that wastes fewer pad columns
         uint64_t slots8 = 0, slots12 = 0;
         for (uint32_t s = 0; s < n_seq; ++s) {

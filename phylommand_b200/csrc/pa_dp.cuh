@@ -597,8 +597,8 @@ pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, cons
 // a pair is written only if its triangle index lies in [first, first+count).
 // Pairs the s16x2 path cannot take (a non-A/C/G/T sequence, or longer than
 // max_len16) are appended to `deferred` as range-relative indices.
-template <int K>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <int K, int MINB = 1>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
                    const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
                    const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
