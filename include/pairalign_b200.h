@@ -159,6 +159,15 @@ int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b,
                             uint8_t *ax, uint8_t *ay, uint32_t cap, uint32_t *alen,
                             pa_pair_result *res);
 
+/* pairalign -a for many pairs at once.  The alignment of pair k comes back as an op string
+ * ops[op_offsets[k] .. op_offsets[k] + n_ops[k]), one byte per aligned column in alignment order:
+ * 0 = a base of x over a base of y, 1 = a base of x over a gap, 2 = a gap over a base of y
+ * (bases are consumed from the encoded sequences in order).  op_offsets (count+1 entries) is filled by
+ * the call with the prefix sum of len(ia[k]) + len(ib[k]); ops_cap must be at least op_offsets[count].
+ * res (optional) receives the pair records.  Pairs are processed in batches sized to device memory. */
+int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
+                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res);
+
 /* Split [first, first+count) into n_parts contiguous ranges with nearly equal
  * DP cells (sum of n*m); bounds gets n_parts+1 ascending pair indices.  Used
  * to shard the triangle over devices / ranks. */

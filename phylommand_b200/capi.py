@@ -52,6 +52,8 @@ SYMBOLS = {
     "pa_align_all_pairs_device": (C.c_int, [C.POINTER(PaParams), C.c_uint64, C.c_uint64, C.c_void_p]),
     "pa_align_pair_traceback": (C.c_int, [C.POINTER(PaParams), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]),
+    "pa_align_pairs_ops": (C.c_int, [C.POINTER(PaParams), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "pa_partition_pairs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "pa_partition_by_length": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pa_count_cells": (C.c_uint64, [C.c_uint64, C.c_uint64]),
@@ -188,6 +190,22 @@ def align_pair_traceback(a: int, b: int, cap: int, **params):
     p = make_params(**params)
     _check(load().pa_align_pair_traceback(C.byref(p), a, b, ax.ctypes.data, ay.ctypes.data, cap, C.byref(alen), res.ctypes.data))
     return ax[:alen.value].copy(), ay[:alen.value].copy(), res[0]
+
+
+def align_pairs_ops(ia, ib, lengths, **params):
+    """pairalign -a for a list of pairs: (ops, offsets, n_ops, records); ops[offsets[k]:offsets[k]+n_ops[k]] is pair k."""
+    ia = np.ascontiguousarray(ia, dtype=np.uint32)
+    ib = np.ascontiguousarray(ib, dtype=np.uint32)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    cap = int((lengths[ia] + lengths[ib]).sum())
+    ops = np.empty(max(cap, 1), dtype=np.uint8)
+    offsets = np.empty(len(ia) + 1, dtype=np.uint64)
+    n_ops = np.empty(len(ia), dtype=np.uint32)
+    res = np.empty(len(ia), dtype=RESULT_DTYPE)
+    p = make_params(**params)
+    _check(load().pa_align_pairs_ops(C.byref(p), ia.ctypes.data, ib.ctypes.data, len(ia), ops.ctypes.data, cap,
+                                     offsets.ctypes.data, n_ops.ctypes.data, res.ctypes.data))
+    return ops, offsets, n_ops, res
 
 
 def partition_pairs(first: int, count: int, n_parts: int) -> np.ndarray:

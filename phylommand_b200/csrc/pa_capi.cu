@@ -69,6 +69,12 @@ struct Device {
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
     uint32_t *d_ia = nullptr, *d_ib = nullptr;
     size_t d_pairs_cap = 0;
+    // pairalign -a: move store, op strings and their offsets for one batch
+    uint8_t *d_dirs = nullptr, *d_ops = nullptr;
+    unsigned long long *d_dirs_off = nullptr, *d_ops_off = nullptr;
+    uint32_t *d_nops = nullptr;
+    pa_pair_result *d_res = nullptr;
+    size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_done[2] = {};
     bool chunk_duo = false, chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
@@ -130,6 +136,9 @@ struct Context {
     uint32_t n_seq = 0;
     std::vector<uint32_t> len;
     Triangle tri;
+    std::vector<uint8_t> host_masks;       // the uploaded 4-bit sets (pa_align_pair_traceback rebuilds strings from them)
+    std::vector<uint64_t> host_offsets;
+    std::vector<uint8_t> host_pure;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
@@ -156,6 +165,7 @@ void free_device(Device &d) {
     if (d.ev_cta) cudaEventDestroy(d.ev_cta);
     for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
     cudaFree(d.d_ia); cudaFree(d.d_ib);
+    cudaFree(d.d_dirs); cudaFree(d.d_ops); cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
     for (auto &e : d.ev) if (e) cudaEventDestroy(e);
     for (auto &e : d.ev_done) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -220,6 +230,30 @@ uint32_t max_len16(const pa_params &p) {
 // Launch the kernels for `count` elements (triangle range starting at `first`,
 // or the explicit lists ia/ib) writing records to d_out (device).  Asynchronous
 // on d.stream; events ev[0..3] bracket the two DP kernels.
+// pairalign -a, pairs with IUPAC codes or '-': the general kernel keeping its moves (2 bits per slot, K = 8)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_general_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
+                       unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
+                       pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off, const int all_pairs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    for (;;) {
+        unsigned long long e = 0;
+        if (lane == 0) e = atomicAdd(work_counter, 1ull);
+        e = __shfl_sync(FULL_MASK, e, 0);
+        if (e >= count) break;
+        const uint32_t a = ia[e], b = ib[e];
+        const int n = (int)S.len[a], m = (int)S.len[b];
+        if (n == 0 || m == 0) {
+            if (lane == 0) { pa_pair_result o; o.score = INT_MIN; o.dist = 0; o.len = 0; o.end_i = n - 1; o.end_j = m - 1; out[e] = o; }
+            continue;
+        }
+        if (!all_pairs && S.pure[a] && S.pure[b]) continue;       // the A/C/G/T kernel has it
+        align_warp<KGEN, true, true>(S.p4 + S.off4[a], n, S.p4 + S.off4[b], m, sc, bbuf, &out[e], lane, dirs + dirs_off[e]);
+    }
+}
+
 // item (pair of pairs) that holds triangle index q
 uint64_t item_of(const Context &c, uint64_t q) {
     uint32_t a, b;
@@ -586,6 +620,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         all_pure = all_pure && pr;
     }
     c.n_seq = n_seq;
+    c.host_masks.assign(masks, masks + offsets[n_seq]);
+    c.host_offsets.assign(offsets, offsets + n_seq + 1);
+    c.host_pure = pure;
     c.len = len;
     c.max_len = max_len;
     c.all_pure = all_pure;
@@ -777,50 +814,146 @@ int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t 
     return align_impl(params, first, count, nullptr, nullptr, nullptr, (pa_pair_result *)d_out);
 }
 
-int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b, uint8_t *ax, uint8_t *ay, uint32_t cap,
-                            uint32_t *alen, pa_pair_result *res) {
+// Bytes of the move store of one pair: n rows of P*W/4 bytes (W = 32*K slots per block), 128-byte aligned.
+static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool pure, bool fast) {
+    const uint64_t W = 32ull * ((pure && fast) ? KFAST : KGEN);
+    const uint64_t P = (m + W - 1) / W;
+    const uint64_t bytes = (uint64_t)n * (P * W / 4);
+    return (bytes + 127) / 128 * 128;
+}
+
+int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
+                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
     int rc = check_params(params);
     if (rc) return rc;
+    if (count == 0) return PA_OK;
+    if (!ia || !ib || !ops || !op_offsets || !n_ops) return fail(PA_EINVAL, "NULL buffer");
     Context &c = *g_ctx;
-    if (a >= c.n_seq || b >= c.n_seq) return fail(PA_ERANGE, "sequence index out of range");
-    if (!ax || !ay || !alen) return fail(PA_EINVAL, "NULL output buffer");
-    const uint32_t n = c.len[a], m = c.len[b];
-    if (cap < n + m) return fail(PA_EINVAL, "alignment buffers need n+m = %u bytes", n + m);
-    if (n == 0 || m == 0) return fail(PA_EINVAL, "empty sequence: the reference's behaviour is undefined here");
+    if (!c.dev[0].p4) return fail(PA_EINVAL, "no sequences uploaded");
+    if (params->aligned) return fail(PA_EINVAL, "pairalign -A prints its input: there is nothing to trace back");
     Device &d = c.dev[0];
     CU(cudaSetDevice(d.id));
-    uint8_t *dirs = nullptr, *rx = nullptr, *ry = nullptr;
-    uint32_t *d_alen = nullptr;
-    pa_pair_result *d_res = nullptr;
-    const size_t cells = (size_t)n * m;
-    cudaError_t e = cudaMalloc(&dirs, cells);
-    if (e == cudaSuccess) e = cudaMalloc(&rx, (size_t)n + m);
-    if (e == cudaSuccess) e = cudaMalloc(&ry, (size_t)n + m);
-    if (e == cudaSuccess) e = cudaMalloc(&d_alen, sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(pa_pair_result));
-    pa_pair_result hres;
-    uint32_t halen = 0;
-    std::vector<uint8_t> hx((size_t)n + m), hy((size_t)n + m);
-    if (e == cudaSuccess) {
-        Scoring sc{params->match, params->mismatch, params->gap_open, params->gap_ext};
-        pa_traceback_kernel<KGEN><<<1, 32, 0, d.stream>>>(store_of(d, c.n_seq), sc, a, b, d.bbuf, dirs, d_res, rx, ry, d_alen);
-        e = cudaGetLastError();
+    const bool fast = fast_params_ok(*params);
+    uint64_t total_ops = 0;
+    for (uint64_t k = 0; k < count; ++k) {
+        if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
+        op_offsets[k] = total_ops;
+        total_ops += (uint64_t)c.len[ia[k]] + c.len[ib[k]];
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-    if (e == cudaSuccess) e = cudaMemcpy(&halen, d_alen, sizeof halen, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(&hres, d_res, sizeof hres, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && halen <= n + m) {
-        e = cudaMemcpy(hx.data(), rx, halen, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(hy.data(), ry, halen, cudaMemcpyDeviceToHost);
+    op_offsets[count] = total_ops;
+    if (total_ops > ops_cap) return fail(PA_EINVAL, "op buffer holds %llu bytes, %llu needed (sum of both lengths over the pairs)",
+                                         (unsigned long long)ops_cap, (unsigned long long)total_ops);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = std::min<uint64_t>((uint64_t)((free_b + d.cap_dirs) / 2), 48ull << 30);
+    const Scoring sc{params->match, params->mismatch, params->gap_open, params->gap_ext};
+    const SeqStore S = store_of(d, c.n_seq);
+    const int threads = WARPS_PER_CTA * 32;
+    std::vector<unsigned long long> h_dirs_off, h_ops_off;
+    uint64_t s0 = 0;
+    while (s0 < count) {
+        // one batch: as many pairs as the move store holds
+        uint64_t e0 = s0, dbytes = 0, obytes = 0;
+        bool any_pure = false, any_general = false;
+        h_dirs_off.clear(); h_ops_off.clear();
+        while (e0 < count && e0 - s0 < (1ull << 20)) {
+            const uint32_t a = ia[e0], b = ib[e0];
+            const bool pure = c.host_pure[a] && c.host_pure[b];
+            const uint64_t need = (c.len[a] && c.len[b]) ? dirs_bytes(c.len[a], c.len[b], pure, fast) : 0;
+            if (dbytes + need > budget) {
+                if (e0 == s0) return fail(PA_ENOMEM, "the moves of pair %llu need %llu bytes; %llu available", (unsigned long long)e0,
+                                          (unsigned long long)need, (unsigned long long)budget);
+                break;
+            }
+            h_dirs_off.push_back(dbytes);
+            h_ops_off.push_back(obytes);
+            dbytes += need;
+            obytes += (uint64_t)c.len[a] + c.len[b];
+            if (pure && fast) any_pure = true; else any_general = true;
+            ++e0;
+        }
+        const uint64_t nb = e0 - s0;
+        auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
+            if (bytes <= cap && *ptr) return cudaSuccess;
+            cudaFree(*ptr); *ptr = nullptr; cap = 0;
+            cudaError_t e = cudaMalloc(ptr, bytes);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        };
+        CU(grow((void **)&d.d_dirs, d.cap_dirs, std::max<uint64_t>(dbytes, 128)));
+        CU(grow((void **)&d.d_ops, d.cap_ops, std::max<uint64_t>(obytes, 128)));
+        if (nb > d.cap_tb_pairs) {
+            cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
+            d.d_dirs_off = d.d_ops_off = nullptr; d.d_nops = nullptr; d.d_res = nullptr; d.cap_tb_pairs = 0;
+            CU(cudaMalloc(&d.d_dirs_off, nb * sizeof(unsigned long long)));
+            CU(cudaMalloc(&d.d_ops_off, nb * sizeof(unsigned long long)));
+            CU(cudaMalloc(&d.d_nops, nb * sizeof(uint32_t)));
+            CU(cudaMalloc(&d.d_res, nb * sizeof(pa_pair_result)));
+            d.cap_tb_pairs = nb;
+        }
+        if (nb > d.d_pairs_cap) {
+            cudaFree(d.d_ia); cudaFree(d.d_ib); d.d_ia = d.d_ib = nullptr; d.d_pairs_cap = 0;
+            CU(cudaMalloc(&d.d_ia, nb * sizeof(uint32_t)));
+            CU(cudaMalloc(&d.d_ib, nb * sizeof(uint32_t)));
+            d.d_pairs_cap = nb;
+        }
+        CU(cudaMemcpyAsync(d.d_ia, ia + s0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.d_ib, ib + s0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.d_dirs_off, h_dirs_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.d_ops_off, h_ops_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), d.stream));
+        CU(cudaMemsetAsync(d.d_res, 0, nb * sizeof(pa_pair_result), d.stream));
+        if (any_pure) {
+            pa_warp32_dirs_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters, d.bbuf, d.bbuf_rows,
+                                                                                d.d_res, d.d_dirs, d.d_dirs_off);
+            CU(cudaGetLastError());
+        }
+        if (any_general) {
+            pa_general_dirs_kernel<<<d.grid_gen, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters + 1, d.bbuf, d.bbuf_rows,
+                                                                         d.d_res, d.d_dirs, d.d_dirs_off, fast ? 0 : 1);
+            CU(cudaGetLastError());
+        }
+        pa_walk_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
+                                                                          d.d_ops_off, d.d_nops, fast ? KFAST : KGEN, KGEN);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ops + op_offsets[s0], d.d_ops, obytes, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemcpyAsync(n_ops + s0, d.d_nops, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (res) CU(cudaMemcpyAsync(res + s0, d.d_res, nb * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        // the walk wrote each op string backwards (the reference reverses at src/seqpair.cpp:183-188)
+        for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);
+        s0 = e0;
     }
-    cudaFree(dirs); cudaFree(rx); cudaFree(ry); cudaFree(d_alen); cudaFree(d_res);
-    if (e != cudaSuccess) return fail(PA_ECUDA, "traceback failed: %s", cudaGetErrorString(e));
-    if (halen > n + m) return fail(PA_ECUDA, "traceback produced %u columns for n+m=%u", halen, n + m);
-    for (uint32_t k = 0; k < halen; ++k) { ax[k] = hx[halen - 1 - k]; ay[k] = hy[halen - 1 - k]; }   // src/seqpair.cpp:183-188
-    *alen = halen;
-    if (res) *res = hres;
+    return PA_OK;
+}
+
+int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b, uint8_t *ax, uint8_t *ay, uint32_t cap,
+                            uint32_t *alen, pa_pair_result *res) {
+    uint32_t n = 0, m = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+        if (a >= g_ctx->n_seq || b >= g_ctx->n_seq) return fail(PA_ERANGE, "sequence index out of range");
+        if (!ax || !ay || !alen) return fail(PA_EINVAL, "NULL output buffer");
+        n = g_ctx->len[a]; m = g_ctx->len[b];
+        if (cap < n + m) return fail(PA_EINVAL, "alignment buffers need n+m = %u bytes", n + m);
+        if (n == 0 || m == 0) return fail(PA_EINVAL, "empty sequence: the reference's behaviour is undefined here");
+    }
+    std::vector<uint8_t> ops((size_t)n + m);
+    uint64_t off[2];
+    uint32_t nops = 0;
+    int rc = pa_align_pairs_ops(params, &a, &b, 1, ops.data(), ops.size(), off, &nops, res);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint8_t *x = g_ctx->host_masks.data() + g_ctx->host_offsets[a], *y = g_ctx->host_masks.data() + g_ctx->host_offsets[b];
+    uint32_t i = 0, j = 0;
+    for (uint32_t k = 0; k < nops; ++k) {
+        ax[k] = ops[k] == 2 ? 0 : x[i++];
+        ay[k] = ops[k] == 1 ? 0 : y[j++];
+    }
+    *alen = nops;
     return PA_OK;
 }
 

@@ -212,6 +212,7 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                     const int sM = xgap ? INT_MIN : sc.match;
                     const int sX = xgap ? INT_MIN : sc.mismatch;
                     const bool row0 = (i == 0);
+                    uint32_t mv = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const uint32_t ym = selS[k];
@@ -236,10 +237,14 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                         if (!xgap && ym != 0) inc = 0x10000u + (both == 0 ? 1u : 0u);
                         uint32_t c = pD ? cd + inc : (pU ? cu : cl);
                         if (fl == 2) c = 0;
-                        if (DIRS && fl != 2) dirs[(size_t)i * (size_t)m + (size_t)(j0 + k)] = pD ? 0 : (pU ? 1 : 2);
+                        if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
                         Hd = H[k]; cd = cu;
                         H[k] = h; Gy[k] = gy; C[k] = c;
                         Gl = gx; cl = c;
+                    }
+                    if (DIRS) {   // 2 bits per slot, row-major, K/4 bytes per lane (K = 8: one 16-bit store)
+                        static_assert(!DIRS || K == 8, "the move store assumes K = 8");
+                        reinterpret_cast<uint16_t *>(dirs)[(size_t)i * ((size_t)P * 32) + (size_t)p * 32 + lane] = (uint16_t)mv;
                     }
                 }
                 hprev = hin; cprev = cin;
@@ -696,39 +701,6 @@ pa_aligned_stats_kernel(const SeqStore S, const PairSource src, const uint64_t c
         }
         if (lane == 0) { pa_pair_result o; o.score = 0; o.dist = d; o.len = l; o.end_i = n - 1; o.end_j = m - 1; out[w] = o; }
     }
-}
-
-// pairalign -a: one pair, moves kept (one byte per cell), then the reference's
-// walk back from the end cell (src/seqpair.cpp:146-178).  rx/ry receive the
-// aligned 4-bit sets in REVERSE order (the reference reverses at :183-188; the
-// host does that), *alen their count.  One warp.
-template <int K>
-__global__ void __launch_bounds__(32)
-pa_traceback_kernel(const SeqStore S, const Scoring sc, const uint32_t a, const uint32_t b, int4 *bbuf,
-                    uint8_t *dirs, pa_pair_result *res, uint8_t *rx, uint8_t *ry, uint32_t *alen) {
-    const int lane = threadIdx.x & 31;
-    const int n = (int)S.len[a], m = (int)S.len[b];
-    const uint32_t *xs = S.p4 + S.off4[a], *ys = S.p4 + S.off4[b];
-    align_warp<K, true, true>(xs, n, ys, m, sc, bbuf, res, lane, dirs);
-    __threadfence_block();
-    __syncwarp();
-    if (lane != 0) return;
-    int i = res->end_i, j = res->end_j;
-    uint32_t k = 0;
-    if (i < n - 1) {
-        for (int pos = n - 1; pos > i; --pos) { rx[k] = (uint8_t)fetch4(xs, pos); ry[k] = 0; ++k; }
-    } else if (j < m - 1) {
-        for (int pos = m - 1; pos > j; --pos) { rx[k] = 0; ry[k] = (uint8_t)fetch4(ys, pos); ++k; }
-    }
-    while (i >= 0 || j >= 0) {
-        uint8_t d = 3;
-        if (i >= 0 && j >= 0) d = dirs[(size_t)i * (size_t)m + (size_t)j];
-        if (d == 0) { rx[k] = (uint8_t)fetch4(xs, i); ry[k] = (uint8_t)fetch4(ys, j); --i; --j; }
-        else if (j < 0 || (i >= 0 && d == 1)) { rx[k] = (uint8_t)fetch4(xs, i); ry[k] = 0; --i; }
-        else { rx[k] = 0; ry[k] = (uint8_t)fetch4(ys, j); --j; }
-        ++k;
-    }
-    *alen = k;
 }
 
 }  // namespace pa

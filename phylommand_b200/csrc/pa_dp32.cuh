@@ -44,13 +44,16 @@ __device__ __forceinline__ void build_tab32(int4 *tab, const Scoring sc, const u
     }
 }
 
-template <int K>
+// DIRS: also return the moves of this lane's K cells, 2 bits each (0 D, 1 U, 2 L), column k in bits 2k..2k+1
+template <int K, bool DIRS = false>
 __device__ __forceinline__ void row32(const int (&Hs)[K], int (&Hd)[K], int (&Gy)[K],
                                       const uint32_t (&Cs)[K], uint32_t (&Cd)[K],
                                       const uint32_t (&selS)[K], const uint32_t (&selI)[K],
                                       const uint32_t Rlo, const uint32_t Rhi, const uint32_t Mlo, const uint32_t Mhi,
                                       const int go, const int ge, int hdiag, int Gl, uint32_t cd, uint32_t cl,
-                                      int &Hout, int &Gxout, uint32_t &cout) {
+                                      int &Hout, int &Gxout, uint32_t &cout, uint32_t &moves) {
+    static_assert(!DIRS || K <= 16, "moves of one lane must fit 32 bits");
+    uint32_t mv = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int s = (int)prmt(Rlo, Rhi, selS[k]);
@@ -65,11 +68,13 @@ __device__ __forceinline__ void row32(const int (&Hs)[K], int (&Hd)[K], int (&Gy
         const bool pU = (gy >= gx);
         const uint32_t cdi = cd + inc;
         const uint32_t c = pD ? cdi : (pU ? cu : cl);
+        if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
         hdiag = Hs[k]; cd = cu;
         Hd[k] = h; Gy[k] = gy; Cd[k] = c;
         Gl = gx; cl = c;
     }
     Hout = Hd[K - 1]; Gxout = Gl; cout = cl;
+    moves = mv;
 }
 
 // Edge policy of the warp kernel: scratch rows in global memory, no waiting.
@@ -143,10 +148,13 @@ struct Best32 {
 };
 
 // One block: columns [j_base, j_base + 32*K) of the pair (j_base may be negative: pad), all n rows.
-template <int K, class Edge>
+// DIRS: moves go to dirp[row * dstride] (this lane's 32-bit word of the row; the caller points dirp at the
+// lane's word of row 0).
+template <int K, class Edge, bool DIRS = false>
 __device__ __forceinline__ void block32(const uint32_t *xs, const int n, const uint32_t *ys, const int j_base,
                                         const bool first_block, const bool last_block, const Scoring sc,
-                                        const int4 *tab, const Edge &edge, const int lane, Best32 &best) {
+                                        const int4 *tab, const Edge &edge, const int lane, Best32 &best,
+                                        uint32_t *dirp = nullptr, const uint32_t dstride = 0) {
     const int Hinit = -sc.go;
     const int j0 = j_base + lane * K;
     int HX[K], HY[K], Gy[K];
@@ -197,15 +205,19 @@ __device__ __forceinline__ void block32(const uint32_t *xs, const int n, const u
             const bool store = (lane == 31) && edge.has_sink();
             {
                 const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
-                row32<K>(HX, HY, Gy, CX, CY, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
-                         sc.go, sc.ge, hprev, ginA, cprev, cinA, HoA, GoA, coA);
+                uint32_t mv;
+                row32<K, DIRS>(HX, HY, Gy, CX, CY, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
+                               sc.go, sc.ge, hprev, ginA, cprev, cinA, HoA, GoA, coA, mv);
+                if (DIRS) dirp[(size_t)iA * dstride] = mv;
                 if (store) edge.store(iA, make_int4(HoA, GoA, (int)coA, 0));
                 if (last_block && HoA > best.colBest) { best.colBest = HoA; best.colI = iA; best.colC = coA; }
             }
             if (iA + 1 < n) {
                 const int4 T = tab[xi2 >> 2];
-                row32<K>(HY, HX, Gy, CY, CX, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
-                         sc.go, sc.ge, hinA, ginB, cinA, cinB, HoB, GoB, coB);
+                uint32_t mv;
+                row32<K, DIRS>(HY, HX, Gy, CY, CX, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
+                               sc.go, sc.ge, hinA, ginB, cinA, cinB, HoB, GoB, coB, mv);
+                if (DIRS) dirp[(size_t)(iA + 1) * dstride] = mv;
                 if (store) edge.store(iA + 1, make_int4(HoB, GoB, (int)coB, 0));
                 if (last_block && HoB > best.colBest) { best.colBest = HoB; best.colI = iA + 1; best.colC = coB; }
             }
@@ -402,6 +414,104 @@ pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const 
             finish32(f, n, m, &out[e]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// pairalign -a.  The DP kernels below also keep the move of every cell, 2 bits
+// per column SLOT (slot = column + pad, the right-aligned layout of the DP),
+// row-major, row stride = P*32*K/4 bytes, at dirs + dirs_off[e].  A second
+// kernel then walks each pair back with one thread per pair.
+//
+// dirs_off[e] == ~0ull marks an element another kernel handles (the A/C/G/T
+// kernel skips pairs with IUPAC codes or gaps and vice versa).
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
+                      unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
+                      pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off) {
+    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
+    __shared__ int4 tabs[WARPS_PER_CTA][8];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
+    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
+    const uint32_t vrow = bbuf_rows - 1;
+    constexpr int W = 32 * K;
+    for (;;) {
+        unsigned long long e = 0;
+        if (lane == 0) e = atomicAdd(work_counter, 1ull);
+        e = __shfl_sync(FULL_MASK, e, 0);
+        if (e >= count) break;
+        const uint32_t a = ia[e], b = ib[e];
+        const int n = (int)S.len[a], m = (int)S.len[b];
+        if (n == 0 || m == 0 || !(S.pure[a] && S.pure[b])) continue;
+        __syncwarp();
+        const uint32_t *xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
+        const uint32_t *ys = stage_seq(S.p2 + S.off2[b], (uint32_t)(m + 15) >> 4, stage[wib][1], lane);
+        build_tab32(tabs[wib], sc, fetch2(S.p2 + S.off2[b], 0), lane);
+        if (lane == 0) __stcg(&bbuf[vrow], make_int4(-sc.go, 0, 0, 0));
+        __syncwarp();
+        const int P = (m + W - 1) / W;
+        const int padL = P * W - m;
+        uint32_t *dpair = reinterpret_cast<uint32_t *>(dirs + dirs_off[e]);
+        Best32 best;
+        best.rowBest = INT_MIN; best.rowJ = INT_MAX; best.rowC = 0;
+        best.colBest = INT_MIN; best.colI = n - 1; best.colC = 0;
+        for (int p = 0; p < P; ++p) {
+            GlobalEdge edge;
+            edge.feed = p > 0 ? bbuf : bbuf + vrow;
+            edge.fmul = p > 0 ? 1 : 0;
+            edge.sink = p < P - 1 ? bbuf : nullptr;
+            block32<K, GlobalEdge, true>(xs, n, ys, p * W - padL, p == 0, p == P - 1, sc, tabs[wib], edge, lane, best,
+                                         dpair + p * 32 + lane, (uint32_t)P * 32u);
+        }
+        best.colBest = __shfl_sync(FULL_MASK, best.colBest, 31);
+        best.colI = __shfl_sync(FULL_MASK, best.colI, 31);
+        best.colC = __shfl_sync(FULL_MASK, best.colC, 31);
+        if (lane == 0) finish32(best, n, m, &out[e]);
+    }
+}
+
+// One thread per pair: the reference's walk (src/seqpair.cpp:146-178).  ops receives one byte per aligned
+// column in the REVERSE order the reference builds them in (it reverses at :183-188; the host does that):
+// 0 = x[i] over y[j], 1 = x[i] over a gap, 2 = gap over y[j].  kcols: strip width of the kernel that wrote the
+// moves of this pair (16 for A/C/G/T pairs, 8 for the general kernel).
+__global__ void pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
+                               const pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
+                               uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
+                               const int k_pure, const int k_general) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t a = ia[e], b = ib[e];
+    const int n = (int)S.len[a], m = (int)S.len[b];
+    uint8_t *o = ops + ops_off[e];
+    uint32_t k = 0;
+    if (n == 0 || m == 0) {       // nothing to align (undefined in the reference): the other sequence against gaps
+        for (int q = 0; q < n; ++q) o[k++] = 1;
+        for (int q = 0; q < m; ++q) o[k++] = 2;
+        n_ops[e] = k;
+        return;
+    }
+    const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : k_general);
+    const int P = (m + W - 1) / W;
+    const int padL = P * W - m;
+    const size_t stride = (size_t)P * W / 4;
+    const uint8_t *d = dirs + dirs_off[e];
+    int i = res[e].end_i, j = res[e].end_j;
+    if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
+    else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
+    while (i >= 0 || j >= 0) {
+        uint32_t mv = 3;
+        if (i >= 0 && j >= 0) {
+            const int slot = j + padL;
+            mv = (d[(size_t)i * stride + (slot >> 2)] >> ((slot & 3) * 2)) & 3u;
+        }
+        if (mv == 0) { o[k++] = 0; --i; --j; }
+        else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
+        else { o[k++] = 2; --j; }
+    }
+    n_ops[e] = k;
 }
 
 }  // namespace pa

@@ -165,6 +165,8 @@ public:
 
     std::function<std::string(const PairView &, int)> taxon_of;   // get_taxon_string of side 1 / 2 (src/seqdatabase.h:106-114)
     std::function<float(long)> comp_of;                           // get_comp_value(accession or lead) (src/seqdatabase.h:97-105)
+    // get_x()/get_y() of the pair being replayed, when a batch of alignments is at hand (mode 'a')
+    std::function<bool(const PairView &, std::string &, std::string &)> alignment_of;
     ClusterStore clusters;
     MadGroups deviations;
 
@@ -185,8 +187,8 @@ public:
         if (mode == 'A' || mode == 'B') group(v, st);
         else if (mode == 'a') {
             std::string x, y;
-            if (v.seq2 >= 0) batch_.alignment(params, (uint32_t)v.seq1, (uint32_t)v.seq2, x, y);
-            else { x = batch_.text((size_t)v.seq1); y.assign(x.size(), '-'); }
+            if (v.seq2 < 0) { x = batch_.text((size_t)v.seq1); y.assign(x.size(), '-'); }
+            else if (!alignment_of || !alignment_of(v, x, y)) batch_.alignment(params, (uint32_t)v.seq1, (uint32_t)v.seq2, x, y);
             if (opt_.output_names) { out_.put('>'); out_.put(*v.accno1); out_.put('\n'); }
             out_.put(x); out_.put('\n');
             if (opt_.output_names) { out_.put('>'); out_.put(*v.accno2); out_.put('\n'); }
@@ -402,10 +404,27 @@ void run_fasta(const Options &opt, Out &out) {
             const bool need_stats = (mode != 'a' && mode != 'C');
             const uint64_t total = (uint64_t)N * (N - 1) / 2;
             if (need_stats || mode == 'a') { init_devices(); batch.upload(); }
+            // mode 'a': batches of alignments (op strings) travel beside the record buffers
+            SeqpairBatch::OpBatch opb[2];
+            std::vector<uint32_t> ia_b, ib_b;
+            uint32_t max_len = 1;
+            for (size_t s = 0; s < N; ++s) max_len = std::max(max_len, batch.length(s));
+            const bool want_ops = (mode == 'a' && !opt.aligned);
+            const uint64_t chunk_pairs = want_ops ? std::max<uint64_t>(1, std::min<uint64_t>(kChunkPairs, (256ull << 20) / (2ull * max_len)))
+                                                  : kChunkPairs;
+            size_t cur_k = 0;
+            int cur_slot = 0;
+            if (want_ops)
+                rp.alignment_of = [&](const PairView &v, std::string &x, std::string &y) {
+                    const SeqpairBatch::OpBatch &ob = opb[cur_slot];
+                    batch.render((uint32_t)v.seq1, (uint32_t)v.seq2, ob.ops.data() + ob.offsets[cur_k], ob.n_ops[cur_k], x, y);
+                    return true;
+                };
             uint32_t a = 0, b = 0;       // pair cursor in reference order: (0,1),(0,2)..(1,2)..
             auto consume = [&](uint64_t first, const std::vector<pa_pair_result> &recs) {
-                (void)first;
+                cur_slot = (int)((first / chunk_pairs) & 1);
                 for (size_t k = 0; k < recs.size(); ++k) {
+                    cur_k = k;
                     if (b == 0) { a = 0; b = 1; }
                     PairView v{&index[a].accno, &index[b].accno, (long)a, (long)b, (long)a, (long)b, b == a + 1};
                     PairStats st{recs[k]};
@@ -416,8 +435,18 @@ void run_fasta(const Options &opt, Out &out) {
             auto produce = [&](uint64_t first, uint64_t n, pa_pair_result *dst) {
                 if (need_stats) batch.align_range(params, first, n, dst);
                 else std::memset(dst, 0, (size_t)n * sizeof(pa_pair_result));
+                if (want_ops) {
+                    ia_b.resize((size_t)n); ib_b.resize((size_t)n);
+                    uint32_t pa = 0, pb = 0;
+                    pa_pair_from_index(first, &pa, &pb);
+                    for (uint64_t k = 0; k < n; ++k) {
+                        ia_b[(size_t)k] = pa; ib_b[(size_t)k] = pb;
+                        if (++pb == N) { ++pa; pb = pa + 1; }
+                    }
+                    batch.alignments(params, ia_b, ib_b, opb[(first / chunk_pairs) & 1]);
+                }
             };
-            pipeline(total, kChunkPairs, produce, consume);
+            pipeline(total, chunk_pairs, produce, consume);
             // src/pairalign.cpp:629-630 -- printed with or without -n
             if (opt.matrix) { out.put('\n'); out.put(index[N - 1].accno); out.put('\n'); }
         }

@@ -82,4 +82,26 @@ void SeqpairBatch::alignment(const pa_params &p, uint32_t a, uint32_t b, std::st
     for (uint32_t k = 0; k < alen; ++k) { x[k] = pa_mask_to_char(ax[k]); y[k] = pa_mask_to_char(ay[k]); }
 }
 
+void SeqpairBatch::alignments(const pa_params &p, const std::vector<uint32_t> &ia, const std::vector<uint32_t> &ib, OpBatch &out) {
+    uint64_t cap = 0;
+    for (size_t k = 0; k < ia.size(); ++k) cap += (uint64_t)length(ia[k]) + length(ib[k]);
+    out.ops.resize(std::max<uint64_t>(cap, 1));
+    out.offsets.resize(ia.size() + 1);
+    out.n_ops.resize(ia.size());
+    if (ia.empty()) return;
+    check(pa_align_pairs_ops(&p, ia.data(), ib.data(), ia.size(), out.ops.data(), cap, out.offsets.data(), out.n_ops.data(), nullptr),
+          "pa_align_pairs_ops");
+}
+
+void SeqpairBatch::render(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, std::string &x, std::string &y) const {
+    const uint8_t *ma = masks(a), *mb = masks(b);
+    x.assign(n_ops, '-');
+    y.assign(n_ops, '-');
+    size_t i = 0, j = 0;
+    for (uint32_t k = 0; k < n_ops; ++k) {
+        if (ops[k] != 2) x[k] = pa_mask_to_char(ma[i++]);
+        if (ops[k] != 1) y[k] = pa_mask_to_char(mb[j++]);
+    }
+}
+
 }  // namespace pab

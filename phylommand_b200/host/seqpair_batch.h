@@ -40,8 +40,17 @@ public:
     // all pairs [first, first+count) of the upper triangle in reference order
     void align_range(const pa_params &p, uint64_t first, uint64_t count, pa_pair_result *out);
     void align_list(const pa_params &p, const std::vector<uint32_t> &ia, const std::vector<uint32_t> &ib, pa_pair_result *out);
-    // get_x()/get_y() after align() (pairalign -a)
+    // get_x()/get_y() after align() (pairalign -a), one pair
     void alignment(const pa_params &p, uint32_t a, uint32_t b, std::string &x, std::string &y);
+    // the same for a batch: op strings (0 both, 1 base over gap, 2 gap over base) of pairs (ia[k], ib[k])
+    struct OpBatch {
+        std::vector<uint8_t> ops;
+        std::vector<uint64_t> offsets;
+        std::vector<uint32_t> n_ops;
+    };
+    void alignments(const pa_params &p, const std::vector<uint32_t> &ia, const std::vector<uint32_t> &ib, OpBatch &out);
+    // turn one op string into the two printed lines
+    void render(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, std::string &x, std::string &y) const;
 
 private:
     std::vector<uint8_t> masks_;

@@ -266,3 +266,34 @@ def test_all_four_dp_kernels_in_one_call(gpu, oracle):
     assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] > 0 and t["dp_cta_ms"] > 0 and t["dp_general_ms"] > 0
     assert t["kernel_launches"] == 4
     _same(got, _oracle_all(oracle, enc, threads=10))
+
+
+def _render(ops, x, y):
+    ax, ay, i, j = [], [], 0, 0
+    for o in ops:
+        ax.append(x[i] if o != 2 else 0); i += (o != 2)
+        ay.append(y[j] if o != 1 else 0); j += (o != 1)
+    assert i == len(x) and j == len(y)
+    return ax, ay
+
+
+def test_batched_alignments(gpu, oracle):
+    """pairalign -a in batches: op strings for A/C/G/T pairs (int32 kernel with 2-bit moves), IUPAC / gap pairs
+    (general kernel) and a multi-block pair, against the reference-literal traceback of the oracle."""
+    _, pure = synth.make_random(10, 701, 5, 700)
+    _, amb = synth.make_random(6, 702, 5, 400, iupac=0.03, gaps=0.02)
+    _, longer = synth.make_long(2, 703, length=2600, spread=0.1)
+    enc = [synth.to_masks(s) for s in pure] + [gpu.encode("N" + synth.to_text(s)) for s in amb] + [synth.to_masks(s) for s in longer]
+    enc = [e if len(e) else np.array([1], dtype=np.uint8) for e in enc]
+    gpu.upload(enc)
+    n = len(enc)
+    ia, ib = np.array([a for a in range(n) for b in range(n) if a != b]), np.array([b for a in range(n) for b in range(n) if a != b])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    stats = gpu.align_pairs(ia, ib)
+    assert res.tobytes() == stats.tobytes()
+    for k in range(len(ia)):
+        r, wx, wy = oracle.align_full(enc[ia[k]], enc[ib[k]])
+        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
+        ax, ay = _render(ops[int(off[k]):int(off[k]) + int(n_ops[k])], enc[ia[k]], enc[ib[k]])
+        assert ax == wx.tolist() and ay == wy.tolist(), (ia[k], ib[k])
