@@ -55,6 +55,10 @@ def workload(name: str, n_gpus: int):
         n = int(round(200 * (n_gpus ** 0.5)))
         names, seqs = synth.make_long(n, 1005)
         label = f"synthetic {n} x 30 kb (seed 1005), all-pairs"
+    elif name == "c5s":
+        n = int(round(16 * (n_gpus ** 0.5)))
+        names, seqs = synth.make_long(n, 1005)
+        label = f"synthetic {n} x 30 kb (seed 1005), all-pairs [profiling size]"
     elif name == "tiny":
         n = int(round(128 * (n_gpus ** 0.5)))
         names, seqs = synth.make_16s_like(n, 1002)
@@ -183,7 +187,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5", "tiny"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5", "c5s", "tiny"])
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")

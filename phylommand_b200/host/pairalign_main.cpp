@@ -16,7 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <unistd.h>
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <functional>
 #include <iostream>
@@ -125,6 +127,18 @@ void print_help() {
               << "--verbose / -v                  get additional output.\n";
     std::cout.flush();
 }
+
+// PAIRALIGN_TIMING=1: wall-clock phases on stderr (not part of the reference's surface)
+struct PhaseTimer {
+    bool on = std::getenv("PAIRALIGN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cerr << "[pairalign_b200] " << what << ": " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms" << std::endl;
+        t0 = t1;
+    }
+};
 
 // ---- buffered stdout with the reference's number formatting -------------------
 // `ostream << double` at default precision is printf("%g").
@@ -347,8 +361,10 @@ constexpr uint64_t kChunkPairs = 1ull << 21;
 
 // ---- fasta input: all pairs of the file -------------------------------------------
 void run_fasta(const Options &opt, Out &out) {
+    PhaseTimer timer;
     FastaIndex index;
     index.open(opt.file_name);
+    timer.mark("read + index FASTA");
     if (!opt.quiet) std::cerr << "Opened " << opt.format << " database." << std::endl;
     std::map<std::string, std::string> taxonomy;
     if (!opt.taxonomy_file.empty()) {
@@ -384,6 +400,7 @@ void run_fasta(const Options &opt, Out &out) {
         std::cerr << "Could not initiate sequence retrieval. No aligning done for " << table << "." << std::endl;
     } else {
         for (size_t s = 0; s < N; ++s) batch.add_sequence(index[s].text);
+        timer.mark("encode sequences");
         rp.clusters.reset(N);
         rp.taxon_of = [&](const PairView &v, int side) {
             const FastaRecord &r = index[(size_t)(side == 1 ? v.seq1 : v.seq2)];
@@ -403,7 +420,12 @@ void run_fasta(const Options &opt, Out &out) {
         } else {
             const bool need_stats = (mode != 'a' && mode != 'C');
             const uint64_t total = (uint64_t)N * (N - 1) / 2;
-            if (need_stats || mode == 'a') { init_devices(); batch.upload(); }
+            if (need_stats || mode == 'a') {
+                init_devices();
+                timer.mark("pa_init (CUDA contexts)");
+                batch.upload();
+                timer.mark("pa_upload_sequences");
+            }
             // mode 'a': batches of alignments (op strings) travel beside the record buffers
             SeqpairBatch::OpBatch opb[2];
             std::vector<uint32_t> ia_b, ib_b;
@@ -447,6 +469,13 @@ void run_fasta(const Options &opt, Out &out) {
                 }
             };
             pipeline(total, chunk_pairs, produce, consume);
+            if (timer.on) {
+                pa_timing tm;
+                if (pa_get_timing(&tm) == PA_OK)
+                    std::cerr << "[pairalign_b200] last batch: kernels " << tm.kernel_ms << " ms, d2h " << tm.d2h_ms << " ms, call "
+                              << tm.total_ms << " ms on " << tm.n_devices << " device(s)" << std::endl;
+            }
+            timer.mark("align + replay (pipelined)");
             // src/pairalign.cpp:629-630 -- printed with or without -n
             if (opt.matrix) { out.put('\n'); out.put(index[N - 1].accno); out.put('\n'); }
         }
@@ -699,8 +728,13 @@ int main(int argc, char *argv[]) {
         std::cerr << "pairalign_b200: " << e.what() << std::endl;
         rc = 2;
     }
-    pa_shutdown();
     rawtime = time(0);
     if (!opt.quiet) std::cerr << "Ended at:" << std::endl << asctime(localtime(&rawtime));
-    return rc;
+    // Everything is written; tearing the CUDA contexts down in order costs seconds on a multi-GPU box
+    // and buys nothing, so leave without it (PAIRALIGN_CLEAN_EXIT=1 keeps the orderly path for sanitizers).
+    std::cout.flush();
+    std::cerr.flush();
+    std::fflush(nullptr);
+    if (std::getenv("PAIRALIGN_CLEAN_EXIT")) { pa_shutdown(); return rc; }
+    _exit(rc);
 }

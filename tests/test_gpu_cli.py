@@ -77,3 +77,15 @@ def test_cli_argument_errors(exe, workdir):
     assert r.returncode == 1
     r = subprocess.run([str(exe), "-g", "nonsense", "pure.fst"], cwd=workdir, capture_output=True)
     assert r.returncode == 1 and b"Do not recognize argument 'nonsense'" in r.stderr
+
+
+def test_cli_two_devices_same_output(exe, workdir):
+    """The in-process multi-device path (one host thread, stream set and pinned buffer per GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    import os
+    want = (CLI_DIR / "pure_j_n_m.out").read_bytes()
+    env = dict(os.environ, PAIRALIGN_DEVICES="0,1")
+    r = subprocess.run([str(exe), "-j", "-n", "-m", "pure.fst"], cwd=workdir, capture_output=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout == want
