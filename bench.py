@@ -47,6 +47,10 @@ def workload(name: str, n_gpus: int):
         n = int(round(1000 * (n_gpus ** 0.5)))
         names, seqs = synth.make_16s_like(n, 1002)
         label = f"synthetic {n} x 1.5 kb 16S-like (seed 1002), all-pairs"
+    elif name == "c3":
+        n = int(round(10000 * (n_gpus ** 0.5)))
+        names, seqs = synth.make_16s_like(n, 1003)
+        label = f"synthetic {n} x 1.5 kb 16S-like (seed 1003), all-pairs"
     elif name == "c4":
         n = int(round(5000 * (n_gpus ** 0.5)))
         names, seqs, _ = synth.make_its_like(n, 1004)
@@ -187,7 +191,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5", "c5s", "tiny"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "c5s", "tiny"])
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
@@ -325,7 +329,7 @@ def main() -> None:
             achieved = OPS_PER_CELL * my_cells / (kern_step_ms * 1e-3) / 1e9
             line["roofline"] = {
                 "bound": "int32", "achieved": achieved, "peak": peak_ops, "unit": "Gop/s", "frac": achieved / peak_ops,
-                "traffic": 7837952,
+                "traffic": 7837952 if (args.workload == "c2" and world == 1) else None,
                 "kernel": "pa_warp_duo_kernel<12> (s16x2 DPX, two pairs per warp, two rows per step)",
                 "kernel_ms_per_step": kern_step_ms, "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL,
