@@ -195,6 +195,30 @@ double pa_jc_distance(uint32_t dist, uint32_t len);
 /* jc_distance()-(1.0-similarity())                         (src/pairalign.cpp:818)   */
 double pa_jc_minus_p(uint32_t dist, uint32_t len);
 
+/* ---- neighbour joining: the consumer of the -m distance matrix ------------- */
+
+/* One join of njtree::build_nj_tree (src/nj_tree.cpp:79-103).  Node ids: 0..n-1 are the
+ * taxa in matrix order, n.. the joins in creation order.  The lengths are the reference's
+ * float expressions (src/nj_tree.cpp:92-94) stored in double like node::branchlength. */
+typedef struct {
+    uint32_t left, right;
+    double   left_len, right_len;
+} pa_nj_join;
+
+#define PA_NJ_MAX_TAXA 65535u
+
+/* Neighbour joining with the reference's arithmetic (float sums in its order, float Q values,
+ * first strictly smallest pair, new node first in the order; src/nj_tree.cpp:32-205) on the
+ * current CUDA device.  dist: row-major upper triangle, n(n-1)/2 floats, as `treeator -n` reads
+ * them from pairalign -m output (read_distance_matrix, src/nj_tree.cpp:252-352).  joins
+ * receives n-2 records; the tree is (root_left:0, root_right:root_right_len)
+ * (src/nj_tree.cpp:193-201).  kernel_ms (optional): CUDA-event time of the joining with the
+ * matrix resident in HBM.  Replaces njtree::build_nj_tree(). */
+int pa_nj_build(const float *dist, uint32_t n, pa_nj_join *joins, uint32_t *root_left,
+                uint32_t *root_right, double *root_right_len, double *kernel_ms);
+/* Kernels launched and algorithmic bytes moved by the last pa_nj_build of this thread. */
+int pa_nj_last_stats(uint64_t *launches, uint64_t *bytes);
+
 /* ---- measurement support ---------------------------------------------------- */
 
 /* INT32 issue-rate micro-benchmark on device 0 of the context: independent

@@ -16,6 +16,7 @@ PKG = ROOT / "phylommand_b200"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libpairalign_b200.so"
 CLI_PATH = ROOT / "build" / "pairalign_b200"
+NJ_CLI_PATH = ROOT / "build" / "treeator_b200"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -69,6 +70,20 @@ def build_cli(force: bool = False) -> Path | None:
     return CLI_PATH
 
 
+def build_nj_cli(force: bool = False) -> Path:
+    """`treeator -n` host program (neighbour joining of the -m matrix) linked against the library."""
+    srcs = sorted((PKG / "host_nj").glob("*.cpp"))
+    deps = srcs + [ROOT / "include" / "pairalign_b200.h", LIB_PATH]
+    if not force and _newer(NJ_CLI_PATH, deps):
+        return NJ_CLI_PATH
+    NJ_CLI_PATH.parent.mkdir(parents=True, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(NJ_CLI_PATH),
+           *map(str, srcs), "-L", str(LIB_DIR), "-lpairalign_b200",
+           "-Wl,-rpath," + str(LIB_DIR), "-Wl,-rpath,$ORIGIN/../phylommand_b200/lib"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return NJ_CLI_PATH
+
+
 def build_oracle() -> None:
     """Test infrastructure: the C restatement and (when /root/reference exists) the
     unmodified reference compiled into oracle/_ref/.  Building the checker is not using it."""
@@ -78,6 +93,7 @@ def build_oracle() -> None:
 def build_all(force: bool = False) -> None:
     build_library(force=force)
     build_cli(force=force)
+    build_nj_cli(force=force)
     build_oracle()
 
 

@@ -63,6 +63,9 @@ SYMBOLS = {
     "pa_jc_distance": (C.c_double, [C.c_uint32, C.c_uint32]),
     "pa_jc_minus_p": (C.c_double, [C.c_uint32, C.c_uint32]),
     "pa_int32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pa_nj_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pa_nj_last_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None
@@ -267,3 +270,23 @@ def jc_distance(dist: int, length: int) -> float:
 
 def jc_minus_p(dist: int, length: int) -> float:
     return load().pa_jc_minus_p(dist, length)
+
+
+NJ_JOIN_DTYPE = np.dtype([("left", "<u4"), ("right", "<u4"), ("left_len", "<f8"), ("right_len", "<f8")])
+
+
+def nj_build(tri) -> dict:
+    """Neighbour joining of a row-major upper-triangle float32 distance matrix (njtree::build_nj_tree).
+    Returns joins (NJ_JOIN_DTYPE, n-2), root_left, root_right, root_right_len, kernel_ms, launches, bytes."""
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    n = int(round((1 + (1 + 8 * len(tri)) ** 0.5) / 2))
+    assert n * (n - 1) // 2 == len(tri), "not a triangle"
+    joins = np.zeros(max(n - 2, 0), dtype=NJ_JOIN_DTYPE)
+    rl, rr = C.c_uint32(), C.c_uint32()
+    rlen, ms = C.c_double(), C.c_double()
+    _check(load().pa_nj_build(tri.ctypes.data, n, joins.ctypes.data if len(joins) else None, C.byref(rl), C.byref(rr),
+                              C.byref(rlen), C.byref(ms)))
+    launches, nbytes = C.c_uint64(), C.c_uint64()
+    load().pa_nj_last_stats(C.byref(launches), C.byref(nbytes))
+    return dict(joins=joins, root_left=rl.value, root_right=rr.value, root_right_len=rlen.value, kernel_ms=ms.value,
+                launches=launches.value, bytes=nbytes.value)

@@ -460,6 +460,9 @@ int check_params(const pa_params *p) {
 }  // namespace
 
 // ============================================================================
+// for the other translation units of the module (pa_nj.cu)
+void pa_internal_set_error(const char *msg) { g_err = msg; }
+
 extern "C" {
 
 int pa_api_version(void) { return PA_API_VERSION; }

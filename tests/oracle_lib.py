@@ -18,6 +18,9 @@ REF_SO = ROOT / "oracle" / "_ref" / "libref_seqpair.so"
 REF_CLI = ROOT / "oracle" / "_ref" / "pairalign"
 REF_CLI_PTHREAD = ROOT / "oracle" / "_ref" / "pairalign_pthread"
 
+REF_TREEATOR = ROOT / "oracle" / "_ref" / "treeator"
+NJ_JOIN_DTYPE = np.dtype([("left", "<u4"), ("right", "<u4"), ("left_len", "<f8"), ("right_len", "<f8")])
+
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("dist", "<u4"), ("len", "<u4"), ("end_i", "<i4"), ("end_j", "<i4")])
 
 
@@ -47,6 +50,22 @@ class Oracle:
         lib.pa_oracle_all_pairs.restype = C.c_int
         lib.pa_oracle_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+
+        lib.nj_oracle_build.restype = C.c_int
+        lib.nj_oracle_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_double)]
+
+    def nj_build(self, tri) -> dict:
+        """njtree::build_nj_tree restated (oracle/nj_oracle.c): same result layout as capi.nj_build."""
+        tri = np.ascontiguousarray(tri, dtype=np.float32)
+        n = int(round((1 + (1 + 8 * len(tri)) ** 0.5) / 2))
+        assert n * (n - 1) // 2 == len(tri)
+        joins = np.zeros(max(n - 2, 0), dtype=NJ_JOIN_DTYPE)
+        rl, rr, rlen = C.c_uint32(), C.c_uint32(), C.c_double()
+        rc = self.lib.nj_oracle_build(tri.ctypes.data, n, joins.ctypes.data if len(joins) else None, C.byref(rl),
+                                      C.byref(rr), C.byref(rlen))
+        assert rc == 0
+        return dict(joins=joins, root_left=rl.value, root_right=rr.value, root_right_len=rlen.value)
 
     def encode(self, text) -> np.ndarray:
         if isinstance(text, str):
@@ -142,3 +161,82 @@ def load_ref():
     if not REF_SO.exists():
         return None
     return RefSeqpair(C.CDLL(str(REF_SO)))
+
+
+# ---- neighbour joining: text in, text out (test-side restatement of the reference's reader and printer) ----
+
+def read_distance_matrix(data: bytes, labels: bool = True):
+    """njtree::read_distance_matrix (src/nj_tree.cpp:252-352) -> (names, float32 upper triangle) or None when
+    matrix_good() (src/nj_tree.cpp:22-30) would fail."""
+    rows, names = [], []
+    new_row, value, n_taxa = True, b"", 0
+    for k, ch in enumerate(data):
+        ch = bytes([ch])
+        at_end = k + 1 == len(data)                   # infile.peek() == EOF: the last character ends a value, unread
+        if ch in (b" ", b"\n", b"\r", b"\t") or at_end:
+            if value:
+                if new_row:
+                    rows.append([])
+                    if labels:
+                        names.append(value.decode("latin-1"))
+                    else:
+                        names.append(str(n_taxa))
+                        rows[-1].append(np.float32(_atof(value)))
+                    n_taxa += 1
+                    if ch not in (b"\n", b"\r"):
+                        new_row = False
+                else:
+                    rows[-1].append(np.float32(_atof(value)))
+                value = b""
+        else:
+            value += ch
+        if ch in (b"\n", b"\r"):
+            new_row = True
+    if rows and rows[-1]:
+        rows.append([])
+        names.append(str(n_taxa))
+    n = len(rows)
+    for k, row in enumerate(rows):
+        if len(row) != n - 1 - k:
+            return None
+    tri = np.array([v for row in rows for v in row], dtype=np.float32)
+    return names, tri
+
+
+def _atof(tok: bytes) -> float:
+    import re
+    m = re.match(rb"[ \t]*[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?|inf(inity)?|nan)", tok, re.I)
+    return float(m.group(0)) if m else 0.0
+
+
+def newick(names, res: dict, branch_lengths: bool = True) -> str:
+    """tree::print_newick (src/tree.cpp:239-279): labels, ':' << fixed << branchlength on every node but the root."""
+    n = len(names)
+    joins = res["joins"]
+    blen = {}
+    for j in joins:
+        blen[int(j["left"])] = float(j["left_len"])
+        blen[int(j["right"])] = float(j["right_len"])
+    blen[res["root_left"]] = 0.0
+    blen[res["root_right"]] = float(res["root_right_len"])
+    out = ["("]
+    # explicit stack: 10 000 taxa would overflow Python's recursion limit
+    st = [(res["root_right"], 0), (None, 3), (res["root_left"], 0)]
+    while st:
+        nid, phase = st.pop()
+        if phase == 3:
+            out.append(",")
+        elif nid < n:
+            out.append(names[nid])
+            if branch_lengths:
+                out.append(":%f" % blen[nid])
+        elif phase == 0:
+            j = joins[nid - n]
+            out.append("(")
+            st += [(nid, 2), (int(j["right"]), 0), (None, 3), (int(j["left"]), 0)]
+        else:
+            out.append(")")
+            if branch_lengths:
+                out.append(":%f" % blen[nid])
+    out.append(");\n")
+    return "".join(out)
