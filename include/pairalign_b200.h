@@ -205,7 +205,7 @@ typedef struct {
     double   left_len, right_len;
 } pa_nj_join;
 
-#define PA_NJ_MAX_TAXA 65535u
+#define PA_NJ_MAX_TAXA 65000u
 
 /* Neighbour joining with the reference's arithmetic (float sums in its order, float Q values,
  * first strictly smallest pair, new node first in the order; src/nj_tree.cpp:32-205) on the

