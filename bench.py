@@ -41,8 +41,10 @@ OPS_PER_CELL = 14          # INT32-pipe operations per DP cell in 
 METRIC = "pairs/sec (all-pairs pairalign: seqpair DP + per-pair distance statistics)"
 
 
-def workload(name: str, n_gpus: int):
+def workload(name: str, n_gpus: int, strong: bool = False):
     from phylommand_b200 import synth
+    if strong:                      # fixed set: the triangle is cut into n_gpus ranges
+        n_gpus = 1
     if name == "c2":
         n = int(round(1000 * (n_gpus ** 0.5)))
         names, seqs = synth.make_16s_like(n, 1002)
@@ -164,7 +166,7 @@ def host_threads() -> int:
 def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
-    names, seqs, label = workload(args.workload, args.gpus)
+    names, seqs, label = workload(args.workload, args.gpus, args.scaling == "strong")
     threads = min(host_threads(), 64)
     k = args.cpu_prefix or cpu_prefix_for(threads)
     times = []
@@ -177,7 +179,7 @@ def run_reference(args, rank: int, world: int) -> None:
     value = res["pairs"] / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "gcups": res["cells"] / (ms * 1e-3) / 1e9,
             "config": {"workload": label, "mode": "-j -n -m (Jukes-Cantor matrix)", "step": res["sample"]},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
@@ -195,6 +197,8 @@ def main() -> None:
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): the set grows with sqrt(N) so every GPU keeps the cells of one; strong: fixed set")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +223,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     capi.init([local_rank])
 
-    names, seqs, label = workload(args.workload, world)
+    names, seqs, label = workload(args.workload, world, args.scaling == "strong")
     enc = [synth.to_masks(s) for s in seqs]
     masks, offsets = capi.pack(enc)
     capi.upload_packed(masks, offsets)
@@ -306,7 +310,7 @@ def main() -> None:
         kern_step_ms = kern_ms / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "gcups": total_cells / (el / args.steps) / 1e9,
             "config": {"workload": label, "mode": "-j -m (Jukes-Cantor matrix inputs: score, mismatches, columns per pair)",
                        "pairs": total_pairs, "cells": total_cells, "scoring": "match 7 / mismatch -5 / gap open -15 / extend -1",
@@ -330,7 +334,7 @@ def main() -> None:
             line["roofline"] = {
                 "bound": "int32", "achieved": achieved, "peak": peak_ops, "unit": "Gop/s", "frac": achieved / peak_ops,
                 "traffic": 7837952 if (args.workload == "c2" and world == 1) else None,
-                "kernel": "pa_warp_duo_kernel<12> (s16x2 DPX, two pairs per warp, two rows per step)",
+                "kernel": "pa_warp_duo_kernel<0> (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per lane chosen per work item)",
                 "kernel_ms_per_step": kern_step_ms, "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL,
                 "achieved_def": "14 integer operations per DP cell (SURVEY.md 8d) x cells of this rank / CUDA-event time of the DP kernels",

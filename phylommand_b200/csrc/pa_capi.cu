@@ -63,7 +63,7 @@ struct Device {
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -142,8 +142,10 @@ struct Context {
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
-    int kduo = KDUO;                   // strip width of the s16x2 kernel
-    int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 overrides the choice (tuning)
+    int kduo = 0;                      // strip width of the s16x2 kernel; 0: per work item (duo_pick_k)
+    int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 forces one width (tuning)
+    uint32_t kduo_mask = DUO_KSET;     // PAIRALIGN_KDUO_SET: bit k set = width k allowed in the per-item choice (tuning)
+    int kduo_step_cost = DUO_STEP_COST;          // PAIRALIGN_KDUO_A: per-step overhead of the cost model, in instructions (tuning)
     int duo_minb = 1;                  // PAIRALIGN_DUO_MINB=3: register-capped build of the s16x2 kernel, 3 CTAs per SM (tuning)
     bool force_cta = false;            // PAIRALIGN_FORCE_CTA=1: every long pair takes a CTA regardless of how many there are
     uint64_t est_long_pairs = 0;       // pairs of the whole triangle with a sequence longer than LONG_LEN
@@ -302,7 +304,11 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const unsigned int *count2 = nullptr;
     if (duo) {
         const uint64_t item_lo = item_of(c, first), item_hi = item_of(c, first + count - 1) + 1;
-        if (c.kduo == 8)
+        if (c.kduo == 0)
+            pa_warp_duo_kernel<0><<<d.grid_duo_auto, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost);
+        else if (c.kduo == 8)
             pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred);
@@ -509,6 +515,8 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_duo3 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
         d.grid_duo8 = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo_auto = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
@@ -517,7 +525,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -527,6 +535,8 @@ int pa_init(const int *devices, int n_dev) {
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
+    if (const char *f = std::getenv("PAIRALIGN_KDUO_SET")) c->kduo_mask = (uint32_t)std::strtoul(f, nullptr, 0);
+    if (const char *f = std::getenv("PAIRALIGN_KDUO_A")) c->kduo_step_cost = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_NO_CTA")) c->no_cta = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_DUO_MINB")) c->duo_minb = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_FORCE_CTA")) c->force_cta = (f[0] == '1');
@@ -635,22 +645,12 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
         c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
     }
-    // strip width of the s16x2 kernel: 12 measured faster than 8 on both the 1.5 kb and the 400-900 bp sets
-    // (fewer pad columns with 8 do not make up for its higher per-step overhead)
-    c.kduo = (c.kduo_forced == 8 || c.kduo_forced == 12) ? c.kduo_forced : KDUO;
+    // strip width of the s16x2 kernel: chosen per work item inside the kernel (0); PAIRALIGN_KDUO=8|12 forces one width
+    c.kduo = (c.kduo_forced == 8 || c.kduo_forced == 12) ? c.kduo_forced : 0;
     {
         uint64_t n_long = 0;
         for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
         c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
-    }
-    {   // column slots are handed out in passes of 32*K: pick the strip width that wastes fewer pad columns
-        uint64_t slots8 = 0, slots12 = 0;
-        for (uint32_t s = 0; s < n_seq; ++s) {
-            slots8 += ((uint64_t)len[s] + 255) / 256 * 256;
-            slots12 += ((uint64_t)len[s] + 383) / 384 * 384;
-        }
-        c.kduo = (slots8 * 100 < slots12 * 97) ? 8 : KDUO;      // K=12 amortises the per-step work better: prefer it unless 8 saves > 3 %
-        if (c.kduo_forced == 8 || c.kduo_forced == 12) c.kduo = c.kduo_forced;
     }
     c.row_items.assign((size_t)n_seq + 1, 0);
     for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;

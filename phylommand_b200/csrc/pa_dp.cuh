@@ -602,12 +602,34 @@ pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, cons
 // a pair is written only if its triangle index lies in [first, first+count).
 // Pairs the s16x2 path cannot take (a non-A/C/G/T sequence, or longer than
 // max_len16) are appended to `deferred` as range-relative indices.
+// Strip width (columns per lane) for a pair whose longer column sequence has m bases.  Column slots come in passes
+// of 32*K and the pad slots of the first pass are computed like real ones, so a fixed K wastes up to a whole pass
+// (m = 400 with K = 12: 768 slots).  Every pass has the same number of wavefront steps and a step costs about
+// step_cost + 32*K issue slots, hence cost(K) ~ passes(K) * (step_cost + 32*K).  step_cost = 256 reproduces the
+// measured K = 8 : K = 12 ratio (shuffle latency and loop overhead weigh more than their ~45 instructions).
+// Widths in use: 8, 10, 11, 12, 13 (DUO_KSET).  K = 9 is left out: its build runs at 2/3 of the speed of its
+// neighbours on the 400-900 bp set (measured, profiles/r01_duo_strip_width.txt); K = 7 never wins.
+constexpr int DUO_KMIN = 8, DUO_KMAX = 13;
+constexpr uint32_t DUO_KSET = (1u << 8) | (1u << 10) | (1u << 11) | (1u << 12) | (1u << 13);
+constexpr int DUO_STEP_COST = 256;
+__host__ __device__ __forceinline__ int duo_pick_k(const int m, const uint32_t kmask, const int step_cost) {
+    int best_k = DUO_KMAX, best = 0x7fffffff;
+#pragma unroll
+    for (int k = DUO_KMAX; k >= DUO_KMIN; --k) {
+        const int cost = ((m + 32 * k - 1) / (32 * k)) * (step_cost + 32 * k);
+        if (((kmask >> k) & 1u) && cost < best) { best = cost; best_k = k; }
+    }
+    return best_k;
+}
+
+// K = 0: the strip width is chosen per work item (duo_pick_k); K > 0: fixed.
 template <int K, int MINB = 1>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
                    const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
                    const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
-                   pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred) {
+                   pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred,
+                   const uint32_t kmask = DUO_KSET, const int step_cost = DUO_STEP_COST) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
     __shared__ int4 tabs[WARPS_PER_CTA][8];
     const int lane = threadIdx.x & 31;
@@ -657,8 +679,19 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         const uint32_t *ys1 = stage_seq(S.p2 + S.off2[y1], (uint32_t)(my1 + 15) >> 4, stage[wib][1], lane);
         const uint32_t *ys2 = stage_seq(S.p2 + S.off2[y2], (uint32_t)(my2 + 15) >> 4, stage[wib][2], lane);
         __syncwarp();
-        align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib],
-                          use1 ? &out[q1 - first] : nullptr, use2 ? &out[q1 + 1 - first] : nullptr, lane);
+        pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
+        if constexpr (K == 0) {
+            // strip width per work item: the fewest issue slots for these lengths (duo_pick_k)
+            switch (duo_pick_k(my1 > my2 ? my1 : my2, kmask & DUO_KSET, step_cost)) {
+                case 8:  align_warp_duo<8>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 10: align_warp_duo<10>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 11: align_warp_duo<11>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 12: align_warp_duo<12>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                default: align_warp_duo<DUO_KMAX>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+            }
+        } else {
+            align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane);
+        }
     }
 }
 

@@ -85,6 +85,26 @@ def test_all_pairs_pure_acgt(gpu, oracle, lo, hi, n, seed):
     assert got32.tobytes() == got.tobytes()
 
 
+def test_every_strip_width_of_the_s16x2_kernel(gpu, oracle):
+    """The s16x2 kernel picks its strip width (8, 10, 11, 12 or 13 columns per lane) per work item from the longer
+    column sequence: lengths on both sides of every switch point, every width, one to five passes."""
+    rng = np.random.default_rng(11)
+    lengths = [1, 200, 256, 257, 320, 321, 352, 353, 384, 385, 416, 417, 512, 513, 640, 641, 704, 705, 768, 769, 832,
+               833, 960, 1056, 1248, 1536, 1537, 1664, 1665]
+    root = synth.BASES[rng.integers(0, 4, size=max(lengths))]
+    enc = []
+    for L in lengths:
+        s = root[:L].copy()
+        k = rng.random(L) < 0.08 * rng.random()
+        s[k] = synth.BASES[rng.integers(0, 4, size=int(k.sum()))]
+        enc.append(synth.to_masks(s))
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_general_ms"] == 0.0
+    _same(got, _oracle_all(oracle, enc))
+
+
 @pytest.mark.parametrize("iupac,gaps,lo,hi,n,seed", [(0.05, 0.0, 1, 60, 40, 5), (0.03, 0.0, 200, 300, 16, 6),
                                                       (0.02, 0.15, 1, 80, 40, 7), (0.0, 0.2, 250, 330, 12, 8)])
 def test_all_pairs_iupac_and_gaps(gpu, oracle, iupac, gaps, lo, hi, n, seed):
