@@ -144,6 +144,7 @@ struct Context {
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
     int kduo = 0;                      // strip width of the s16x2 kernel; 0: per work item (duo_pick_k)
     int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 forces one width (tuning)
+    bool no_win = false;               // PAIRALIGN_NO_WIN=1: long pairs go to the int32 kernels as before (tuning, tests)
     uint32_t kduo_mask = DUO_KSET;     // PAIRALIGN_KDUO_SET: bit k set = width k allowed in the per-item choice (tuning)
     int kduo_step_cost = DUO_STEP_COST;          // PAIRALIGN_KDUO_A: per-step overhead of the cost model, in instructions (tuning)
     int duo_minb = 1;                  // PAIRALIGN_DUO_MINB=3: register-capped build of the s16x2 kernel, 3 CTAs per SM (tuning)
@@ -296,6 +297,14 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const bool fast = fast_params_ok(p);
     const uint32_t l16 = fast ? max_len16(p) : 0;
     const bool duo = fast && !d_ia && l16 >= 16 && !c.force_32bit;
+    // a CTA per pair pays off when there are too few long pairs to keep every warp of a one-item-per-warp kernel
+    // busy; with thousands of them those kernels are the faster ones (no hand-over, no block-count rounding)
+    const bool route_long = c.max_len > LONG_LEN && !c.no_cta &&
+                            (c.force_cta || c.est_long_pairs < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
+    // pairs too long for plain 16-bit scores stay on the s16x2 kernel (floating-window variant) unless they go to the
+    // CTA kernel; the edge rows then take two bbuf entries each
+    const bool win = duo && c.kduo == 0 && !c.no_win && c.max_len > l16 && !route_long &&
+                     (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;
     CU(cudaEventRecord(d.ev[0], d.stream));
@@ -307,7 +316,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         if (c.kduo == 0)
             pa_warp_duo_kernel<0><<<d.grid_duo_auto, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
-                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost);
+                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0);
         else if (c.kduo == 8)
             pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
@@ -323,7 +332,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         CU(cudaGetLastError());
         d.launches += 1;
         d.chunk_duo = true;
-        stage2 = !c.all_pure || c.max_len > l16;       // something may have been deferred
+        stage2 = !c.all_pure || (c.max_len > l16 && !win);       // something may have been deferred
         src2.idx = d.deferred;
         count2 = d.n_deferred;
     } else if (fast) {
@@ -331,10 +340,6 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     }
     CU(cudaEventRecord(d.ev[1], d.stream));
     if (stage2) {
-        // a CTA per pair pays off when there are too few long pairs to keep every warp of the one-pair-per-warp
-        // kernel busy; with thousands of them that kernel is the faster one (no hand-over, no block-count rounding)
-        const bool route_long = c.max_len > LONG_LEN && !c.no_cta &&
-                                (c.force_cta || c.est_long_pairs < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
         pa_warp32_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(
             S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1,
             route_long ? d.deferred3 : nullptr, d.n_deferred + 2, LONG_LEN);
@@ -538,6 +543,7 @@ int pa_init(const int *devices, int n_dev) {
     if (const char *f = std::getenv("PAIRALIGN_KDUO_SET")) c->kduo_mask = (uint32_t)std::strtoul(f, nullptr, 0);
     if (const char *f = std::getenv("PAIRALIGN_KDUO_A")) c->kduo_step_cost = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_NO_CTA")) c->no_cta = (f[0] == '1');
+    if (const char *f = std::getenv("PAIRALIGN_NO_WIN")) c->no_win = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_DUO_MINB")) c->duo_minb = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_FORCE_CTA")) c->force_cta = (f[0] == '1');
     g_ctx = c;
@@ -675,6 +681,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         CU(grow((void **)&d.len, d.cap_len, nidx * 4));
         CU(grow((void **)&d.pure, d.cap_pure, nidx));
         d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
+        if (max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
         CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
         CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.p2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice, d.stream));

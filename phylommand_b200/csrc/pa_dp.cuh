@@ -372,7 +372,16 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
 // tab: this warp's 8-entry shared table, tab[z*4 + x] = (Rlo, Rhi, Mlo, Mhi) for row code x, z = 1 for
 // row 0 (scores carry +GO there).  vrow: index of the spare scratch row that holds the virtual column
 // left of column 0, so that pass 0 and later passes feed lane 0 through the same loads.
-template <int K>
+// WIN (floating window): scores of long pairs do not fit 16 bits, but the values a lane holds at any moment (K
+// columns x 2 rows, plus what its neighbour hands over) lie within a few hundred of each other -- every state is at
+// most one gap opening away from its diagonal neighbour.  Each lane therefore keeps its halves relative to its own
+// 32-bit offsets (off1, off2: true value = stored + offset), converts what it receives from the left lane's frame
+// into its own (one packed add per value and step), and re-bases by WIN_Q whenever its right-edge value leaves
+// +-WIN_T.  The recurrence itself is untouched: it only ever combines values of one frame.  The edge rows handed to
+// the next pass carry their offsets in a second int4 (bbuf rows 2i, 2i+1), maxima are compared as true 32-bit values.
+constexpr int WIN_T = 8192, WIN_Q = 4096;
+
+template <int K, bool WIN = false>
 __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
                                                const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
                                                const uint32_t vrow, int4 *tab,
@@ -389,6 +398,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
     uint32_t rowC1 = 0, rowC2 = 0;
     // last-column maxima of both pairs, packed like the scores; -32768 stands for "nothing yet"
     uint32_t colBestPk = 0x80008000u;
+    int colB1 = INT_MIN, colB2 = INT_MIN;      // WIN: the same maxima as true 32-bit values
     int colI1 = n - 1, colI2 = n - 1;
     uint32_t colC1 = 0, colC2 = 0;
 
@@ -407,7 +417,10 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             e.w = (int)(0x00010000u | (xi != y10 ? 1u : 0u) | (xi != y20 ? 0x01000000u : 0u));
             tab[z * 4 + xi] = e;
         }
-        if (lane == 0) __stcg(&bbuf[vrow], make_int4((int)HinitPk, 0, 0, 0));
+        if (lane == 0) {
+            __stcg(&bbuf[vrow], make_int4((int)HinitPk, 0, 0, 0));
+            if (WIN) __stcg(&bbuf[vrow + 1], make_int4(0, 0, 0, 0));
+        }
         __syncwarp();
     }
     const int n_steps = ((n + 1) >> 1) + 31;        // two rows per step, lanes one step apart
@@ -437,8 +450,11 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
         uint32_t HoA = HinitPk, GoA = 0, c1oA = 0, c2oA = 0, HoB = HinitPk, GoB = 0, c1oB = 0, c2oB = 0;
         // lane 0's left edge: rows of the previous pass's right edge, or the virtual row in pass 0
         const int4 *feed = p > 0 ? bbuf : bbuf + vrow;
-        const int fmul = p > 0 ? 1 : 0;
+        const int fmul = p > 0 ? (WIN ? 2 : 1) : 0;
         int4 fA = __ldcg(&feed[0]), fB = __ldcg(&feed[fmul * (n > 1 ? 1 : 0)]);
+        int4 fOA = make_int4(0, 0, 0, 0), fOB = fOA;       // WIN: the offsets of the two feed rows
+        if (WIN) { fOA = __ldcg(&feed[1]); fOB = __ldcg(&feed[fmul * (n > 1 ? 1 : 0) + 1]); }
+        int off1 = 0, off2 = 0;
         uint32_t xw = xs[min(max(-2 * lane, 0) >> 4, x_last_word)];
 
         for (int t = 0; t < n_steps; ++t) {
@@ -451,9 +467,21 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                 hinA = (uint32_t)fA.x; ginA = (uint32_t)fA.y; c1inA = (uint32_t)fA.z; c2inA = (uint32_t)fA.w;
                 hinB = (uint32_t)fB.x; ginB = (uint32_t)fB.y; c1inB = (uint32_t)fB.z; c2inB = (uint32_t)fB.w;
             }
+            if (WIN) {   // from the left lane's frame (lane 0: the frames the two edge rows were stored in) into mine
+                int oA1 = __shfl_up_sync(FULL_MASK, off1, 1), oA2 = __shfl_up_sync(FULL_MASK, off2, 1);
+                int oB1 = oA1, oB2 = oA2;
+                if (lane == 0) { oA1 = fOA.x; oA2 = fOA.y; oB1 = fOB.x; oB2 = fOB.y; }
+                const uint32_t dA = pack16(oA1 - off1, oA2 - off2), dB = pack16(oB1 - off1, oB2 - off2);
+                hinA = __vadd2(hinA, dA); ginA = __vadd2(ginA, dA);
+                hinB = __vadd2(hinB, dB); ginB = __vadd2(ginB, dB);
+            }
             // prefetch lane 0's next two rows (every lane issues the same address) and this lane's next x word
             fA = __ldcg(&feed[fmul * min(2 * t + 2, n - 1)]);
             fB = __ldcg(&feed[fmul * min(2 * t + 3, n - 1)]);
+            if (WIN) {
+                fOA = __ldcg(&feed[fmul * min(2 * t + 2, n - 1) + 1]);
+                fOB = __ldcg(&feed[fmul * min(2 * t + 3, n - 1) + 1]);
+            }
             const uint32_t xi2 = (xw >> ((iA & 15) * 2)) & 15u;
             xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
             if (iA >= 0 && iA < n) {
@@ -463,12 +491,23 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     duo_row<K>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
                                (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
                                hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
-                    if (store) __stcg(&bbuf[iA], make_int4((int)HoA, (int)GoA, (int)c1oA, (int)c2oA));
+                    if (store) {
+                        if (WIN) {
+                            __stcg(&bbuf[2 * iA], make_int4((int)HoA, (int)GoA, (int)c1oA, (int)c2oA));
+                            __stcg(&bbuf[2 * iA + 1], make_int4(off1, off2, 0, 0));
+                        } else __stcg(&bbuf[iA], make_int4((int)HoA, (int)GoA, (int)c1oA, (int)c2oA));
+                    }
                     if (last_pass) {   // last column, rows ascending, strict >; every lane tracks, lane 31 is read
-                        bool ghi, glo;                               // best >= candidate: keep
-                        colBestPk = vibmax_s16x2(colBestPk, HoA, ghi, glo);
-                        if (!glo) { colI1 = iA; colC1 = c1oA; }
-                        if (!ghi) { colI2 = iA; colC2 = c2oA; }
+                        if (WIN) {
+                            const int t1 = lo16(HoA) + off1, t2 = hi16(HoA) + off2;
+                            if (t1 > colB1) { colB1 = t1; colI1 = iA; colC1 = c1oA; }
+                            if (t2 > colB2) { colB2 = t2; colI2 = iA; colC2 = c2oA; }
+                        } else {
+                            bool ghi, glo;                               // best >= candidate: keep
+                            colBestPk = vibmax_s16x2(colBestPk, HoA, ghi, glo);
+                            if (!glo) { colI1 = iA; colC1 = c1oA; }
+                            if (!ghi) { colI2 = iA; colC2 = c2oA; }
+                        }
                     }
                 }
                 if (iA + 1 < n) {   // odd row iA+1: previous row in Y, result in X
@@ -476,15 +515,42 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     duo_row<K>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
                                (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
                                hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
-                    if (store) __stcg(&bbuf[iA + 1], make_int4((int)HoB, (int)GoB, (int)c1oB, (int)c2oB));
+                    if (store) {
+                        if (WIN) {
+                            __stcg(&bbuf[2 * iA + 2], make_int4((int)HoB, (int)GoB, (int)c1oB, (int)c2oB));
+                            __stcg(&bbuf[2 * iA + 3], make_int4(off1, off2, 0, 0));
+                        } else __stcg(&bbuf[iA + 1], make_int4((int)HoB, (int)GoB, (int)c1oB, (int)c2oB));
+                    }
                     if (last_pass) {
-                        bool ghi, glo;
-                        colBestPk = vibmax_s16x2(colBestPk, HoB, ghi, glo);
-                        if (!glo) { colI1 = iA + 1; colC1 = c1oB; }
-                        if (!ghi) { colI2 = iA + 1; colC2 = c2oB; }
+                        if (WIN) {
+                            const int t1 = lo16(HoB) + off1, t2 = hi16(HoB) + off2;
+                            if (t1 > colB1) { colB1 = t1; colI1 = iA + 1; colC1 = c1oB; }
+                            if (t2 > colB2) { colB2 = t2; colI2 = iA + 1; colC2 = c2oB; }
+                        } else {
+                            bool ghi, glo;
+                            colBestPk = vibmax_s16x2(colBestPk, HoB, ghi, glo);
+                            if (!glo) { colI1 = iA + 1; colC1 = c1oB; }
+                            if (!ghi) { colI2 = iA + 1; colC2 = c2oB; }
+                        }
                     }
                 }
                 hprev = hinB; c1prev = c1inB; c2prev = c2inB;
+                if (WIN) {   // keep this lane's window centred on its right edge
+                    const uint32_t edge = (iA + 1 < n) ? HoB : HoA;
+                    const int v1 = lo16(edge), v2 = hi16(edge);
+                    const int d1 = v1 > WIN_T ? WIN_Q : (v1 < -WIN_T ? -WIN_Q : 0);
+                    const int d2 = v2 > WIN_T ? WIN_Q : (v2 < -WIN_T ? -WIN_Q : 0);
+                    if (d1 | d2) {
+                        const uint32_t dPk = pack16(d1, d2);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            HX[k] = __vsub2(HX[k], dPk); HY[k] = __vsub2(HY[k], dPk); Gy[k] = __vsub2(Gy[k], dPk);
+                        }
+                        hprev = __vsub2(hprev, dPk);
+                        HoA = __vsub2(HoA, dPk); GoA = __vsub2(GoA, dPk); HoB = __vsub2(HoB, dPk); GoB = __vsub2(GoB, dPk);
+                        off1 += d1; off2 += d2;
+                    }
+                }
             }
         }
         __syncwarp();
@@ -497,7 +563,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
             const uint32_t hk = in_y ? HY[k] : HX[k];
             const uint32_t ck1 = in_y ? C1Y[k] : C1X[k], ck2 = in_y ? C2Y[k] : C2X[k];
-            const int h1 = lo16(hk), h2 = hi16(hk);
+            const int h1 = lo16(hk) + (WIN ? off1 : 0), h2 = hi16(hk) + (WIN ? off2 : 0);
             if (j1 >= 0 && h1 > bv1) { bv1 = h1; bj1 = j1; bc1 = ck1; }
             if (j2 >= 0 && h2 > bv2) { bv2 = h2; bj2 = j2; bc2 = ck2; }
         }
@@ -514,11 +580,12 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
         if (bj2 != INT_MAX && bv2 > rowBest2) { rowBest2 = bv2; rowJ2 = bj2; rowC2 = bc2; }
     }
     colBestPk = __shfl_sync(FULL_MASK, colBestPk, 31);
+    colB1 = __shfl_sync(FULL_MASK, colB1, 31); colB2 = __shfl_sync(FULL_MASK, colB2, 31);
     colI1 = __shfl_sync(FULL_MASK, colI1, 31); colC1 = __shfl_sync(FULL_MASK, colC1, 31);
     colI2 = __shfl_sync(FULL_MASK, colI2, 31); colC2 = __shfl_sync(FULL_MASK, colC2, 31);
     if (lane == 0) {
         // scores stay far above -32768 (host-checked range), so the sentinel is never a real value
-        const int colBest1 = lo16(colBestPk), colBest2 = hi16(colBestPk);
+        const int colBest1 = WIN ? colB1 : lo16(colBestPk), colBest2 = WIN ? colB2 : hi16(colBestPk);
         pa_pair_result o;
         if (res1) {
             if (rowBest1 > colBest1) { o.score = rowBest1; o.end_i = n - 1; o.end_j = rowJ1; o.dist = rowC1 & 0xffffu; o.len = rowC1 >> 16; }
@@ -629,7 +696,7 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
                    const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
                    const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
                    pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred,
-                   const uint32_t kmask = DUO_KSET, const int step_cost = DUO_STEP_COST) {
+                   const uint32_t kmask = DUO_KSET, const int step_cost = DUO_STEP_COST, const int win_ok = 0) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
     __shared__ int4 tabs[WARPS_PER_CTA][8];
     const int lane = threadIdx.x & 31;
@@ -661,9 +728,11 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         if (b2 >= N) b2 = b1;
         const int n = (int)S.len[a], m1 = (int)S.len[b1], m2 = (int)S.len[b2];
         // pairs this path cannot take go to the general / 32-bit kernels
-        const bool okx = S.pure[a] && n > 0 && (uint32_t)n <= max_len16;
-        const bool ok1 = okx && S.pure[b1] && m1 > 0 && (uint32_t)m1 <= max_len16;
-        const bool ok2 = okx && S.pure[b2] && m2 > 0 && (uint32_t)m2 <= max_len16;
+        // longer than max_len16: floating-window variant (K = 0 kernel, when the host allows it), else deferred
+        const uint32_t lim = (K == 0 && win_ok) ? 0xffffffffu : max_len16;
+        const bool okx = S.pure[a] && n > 0 && (uint32_t)n <= lim;
+        const bool ok1 = okx && S.pure[b1] && m1 > 0 && (uint32_t)m1 <= lim;
+        const bool ok2 = okx && S.pure[b2] && m2 > 0 && (uint32_t)m2 <= lim;
         if (lane == 0) {
             if (use1 && !ok1) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 - first);
             if (use2 && !ok2) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 + 1 - first);
@@ -681,6 +750,11 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         __syncwarp();
         pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
         if constexpr (K == 0) {
+            if ((uint32_t)n > max_len16 || (uint32_t)my1 > max_len16 || (uint32_t)my2 > max_len16) {
+                // bbuf rows come in pairs here (values, offsets); the virtual-column row is the last pair
+                align_warp_duo<12, true>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane);
+                continue;
+            }
             // strip width per work item: the fewest issue slots for these lengths (duo_pick_k)
             switch (duo_pick_k(my1 > my2 ? my1 : my2, kmask & DUO_KSET, step_cost)) {
                 case 8:  align_warp_duo<8>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;

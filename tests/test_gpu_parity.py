@@ -240,18 +240,43 @@ def test_long_pair_many_passes(gpu, oracle):
 
 
 def test_s16x2_kernel_near_its_int16_limit(gpu, oracle):
-    """4.5 kb sequences: scores reach 31,500 (identical pair) and stay inside int16; longer ones fall back to 32 bit."""
+    """4.5 kb sequences: scores reach 31,500 (identical pair) and stay inside int16; a longer one switches its work
+    items to the floating-window variant of the same kernel."""
     _, seqs = synth.make_long(3, 77, length=4450, spread=0.02, div_lo=0.0, div_hi=0.05)
     enc = [synth.to_masks(s) for s in seqs]
     enc.append(enc[0].copy())                       # identical to sequence 0: the highest possible score
     _, longer = synth.make_long(1, 78, length=4700, spread=0.0)
-    enc.append(synth.to_masks(longer[0]))           # above max_len16 = 4571: deferred to the 32-bit kernel
+    enc.append(synth.to_masks(longer[0]))           # above max_len16 = 4571: floating-window variant
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     t = gpu.timing()
-    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] > 0
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_cta_ms"] == 0.0
     _same(got, _oracle_all(oracle, enc))
     assert int(got[2]["score"]) == 7 * len(enc[0])  # pair (0, 3)
+
+
+def test_floating_window_s16x2_long_pairs(gpu, oracle):
+    """Pairs of 5-8 kb on the s16x2 kernel: true scores far outside int16 (an identical 8 kb pair scores 56 000, an
+    unrelated one goes negative), every lane re-bases its 16-bit window many times, edge rows carry their offsets
+    from pass to pass; mixed with short partners, odd lengths, and a sequence against its own prefix."""
+    rng = np.random.default_rng(808)
+    _, related = synth.make_long(3, 808, length=7000, spread=0.12, div_lo=0.0, div_hi=0.1)
+    enc = [synth.to_masks(s) for s in related]
+    enc.append(enc[0].copy())                                            # identical: 7 * len
+    enc.append(synth.to_masks(synth.BASES[rng.integers(0, 4, size=8191)]))   # unrelated, odd length
+    enc.append(synth.to_masks(synth.BASES[rng.integers(0, 4, size=5001)]))
+    enc.append(enc[1][:4000].copy())                                     # prefix of a long one (short partner)
+    enc.append(enc[2][1500:1537].copy())                                 # a 37-base piece
+    enc.append(enc[0][::-1].copy())                                      # reversed: no long diagonal at all
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_cta_ms"] == 0.0 and t["kernel_launches"] == 1
+    _same(got, _oracle_all(oracle, enc, threads=12))
+    assert int(got[2]["score"]) == 7 * len(enc[0]) > 32767               # pair (0, 3)
+    # the int32 one-pair-per-warp kernel (explicit pair list) agrees
+    ab = np.array([gpu.pair_from_index(k) for k in range(len(got))])
+    assert gpu.align_pairs(ab[:, 0], ab[:, 1]).tobytes() == got.tobytes()
 
 
 def test_cta_per_pair_kernel_long_pairs(gpu, oracle):
