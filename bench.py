@@ -65,6 +65,10 @@ def workload(name: str, n_gpus: int, strong: bool = False):
         n = int(round(16 * (n_gpus ** 0.5)))
         names, seqs = synth.make_long(n, 1005)
         label = f"synthetic {n} x 30 kb (seed 1005), all-pairs [profiling size]"
+    elif name == "c5w":
+        n = int(round(64 * (n_gpus ** 0.5)))
+        names, seqs = synth.make_long(n, 1005, length=7600, spread=0.05)
+        label = f"synthetic {n} x 7.6 kb (seed 1005), all-pairs [profiling size of the floating-window s16x2 path]"
     elif name == "tiny":
         n = int(round(128 * (n_gpus ** 0.5)))
         names, seqs = synth.make_16s_like(n, 1002)
@@ -193,7 +197,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "c5s", "tiny"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "c5s", "c5w", "tiny"])
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
@@ -333,7 +337,7 @@ def main() -> None:
             achieved = OPS_PER_CELL * my_cells / (kern_step_ms * 1e-3) / 1e9
             line["roofline"] = {
                 "bound": "int32", "achieved": achieved, "peak": peak_ops, "unit": "Gop/s", "frac": achieved / peak_ops,
-                "traffic": 7837952 if (args.workload == "c2" and world == 1) else None,
+                "traffic": 7169024 if (args.workload == "c2" and world == 1) else None,
                 "kernel": "pa_warp_duo_kernel<0> (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per lane chosen per work item)",
                 "kernel_ms_per_step": kern_step_ms, "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL,
@@ -342,7 +346,7 @@ def main() -> None:
                             "all SMs, measured in this run by pa_int32_peak",
                 "frac_vs_32bit_lane_roofline": achieved / alu32, "peak_32bit_lane": alu32,
                 "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                               "(profiles/r01_v3_duo12_ncu_full.txt); algorithmic bytes per launch are in hbm.algorithmic_bytes_per_step",
+                               "(profiles/r01_v4_duo_auto_ncu_full.txt: 1.40 MB read + 5.77 MB written); algorithmic bytes per launch are in hbm.algorithmic_bytes_per_step",
                 "measured": {k: {"gops": v[0], "sm_mhz": v[1]} for k, v in peak.items()},
                 "hbm": {"algorithmic_bytes_per_step": int(masks.nbytes // 4 + count * 20),
                         "note": "2-bit sequences + 20 B per pair; HBM is not the bound (SURVEY.md 8d)"},
