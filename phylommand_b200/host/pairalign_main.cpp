@@ -440,7 +440,9 @@ void run_fasta(const Options &opt, Out &out) {
             const bool need_stats = (mode != 'a' && mode != 'C');
             const uint64_t total = (uint64_t)N * (N - 1) / 2;
             if (need_stats || mode == 'a') {
-                init_devices();
+                double sum = 0, sum2 = 0;                       // DP cells of all pairs: ((sum len)^2 - sum len^2) / 2
+                for (size_t s = 0; s < N; ++s) { const double l = batch.length(s); sum += l; sum2 += l * l; }
+                init_devices(opt.aligned ? 0.0 : (sum * sum - sum2) / 2);
                 timer.mark("pa_init (CUDA contexts)");
                 batch.upload();
                 timer.mark("pa_upload_sequences");
@@ -601,7 +603,9 @@ void run_pairfasta(const Options &opt, Out &out) {
     pa_params params{7, -5, -15, -1, opt.aligned ? 1 : 0};
     std::vector<pa_pair_result> recs(pairs.size());
     if (!pairs.empty() && mode != 'C') {
-        init_devices();
+        double cells = 0;
+        for (size_t k = 0; k < ia.size(); ++k) cells += (double)batch.length(ia[k]) * (double)batch.length(ib[k]);
+        init_devices(opt.aligned ? 0.0 : cells);
         batch.upload();
         if (mode != 'a') batch.align_list(params, ia, ib, recs.data());
     }

@@ -1,5 +1,6 @@
 #include "seqpair_batch.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
@@ -10,7 +11,7 @@ static void check(int rc, const char *what) {
     if (rc != PA_OK) throw std::runtime_error(std::string(what) + ": " + pa_last_error());
 }
 
-void init_devices() {
+void init_devices(double est_cells) {
     std::vector<int> ids;
     if (const char *env = std::getenv("PAIRALIGN_DEVICES")) {
         std::string s(env), tok;
@@ -19,7 +20,12 @@ void init_devices() {
             else tok += s[k];
         }
     } else {
-        const int n = pa_visible_devices();
+        // A CUDA context costs ~0.3 s per extra device: take one device per ~0.5 s of single-GPU work (1.2e12 DP cells)
+        int n = pa_visible_devices();
+        if (est_cells >= 0) {
+            const double want = std::ceil(est_cells / 1.2e12);
+            if (want < n) n = want < 1 ? 1 : (int)want;
+        }
         for (int k = 0; k < n; ++k) ids.push_back(k);
     }
     check(pa_init(ids.empty() ? nullptr : ids.data(), (int)ids.size()), "pa_init");

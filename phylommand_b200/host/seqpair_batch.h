@@ -61,6 +61,7 @@ private:
 
 // pa_init on the devices named by PAIRALIGN_DEVICES (comma separated) or on every
 // visible device; throws std::runtime_error when there is none (no CPU fallback)
-void init_devices();
+// devices from PAIRALIGN_DEVICES, else as many of the visible ones as the work justifies (est_cells < 0: all)
+void init_devices(double est_cells = -1.0);
 
 }  // namespace pab
