@@ -184,7 +184,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned int parity) {
 
 constexpr int NJ_W = 32;                       // columns per warp: one column per lane
 constexpr int NJ_TR = NJ_TILE / NJ_W;          // rows per tile (64)
-constexpr int NJ_STAGES_DEFAULT = 6;           // 8 KB tiles: 5 of them (40 KB) in flight per warp, 4 warps per SM
+constexpr int NJ_STAGES = 6;                   // 8 KB tiles: 5 of them (40 KB) in flight per warp, 4 warps per SM;
+                                               // 3, 12 and 24 stages measured the same (the add chain paces the warp)
 
 // The join itself (src/nj_tree.cpp:79-176), one thread per slot: the new node's row and column
 // (d_ki + d_kj - d_ij) / 2 in the free slot in front, zeroes in the rows and columns of the two joined taxa, and
@@ -226,7 +227,6 @@ struct SumArgs {
 // per 8 KB tile, issued by lane 0) that complete on the stage's mbarrier: no CTA-wide barrier, no per-element copy
 // instructions.  Per row a warp issues one shared load and one FADD; the loads run ahead of the adds, so the only
 // latency left on the critical path is the dependent FADD (7 cycles per row measured with the load, tools/micro).
-template <int NJ_STAGES>
 __global__ void __launch_bounds__(32) nj_sums(const SumArgs g, const __grid_constant__ CUtensorMap tmap) {
     constexpr int W = NJ_W, TR = NJ_TR;
     extern __shared__ __align__(128) float tile[];         // [NJ_STAGES][TR][W]
@@ -264,17 +264,10 @@ __global__ void __launch_bounds__(32) nj_sums(const SumArgs g, const __grid_cons
     g.S2[b] = dead_b ? neg_inf() : s;           // columns past P are dead: -inf
 }
 
-int g_nj_stages = NJ_STAGES_DEFAULT;            // PAIRALIGN_NJ_STAGES=3|6|12|24 (tuning)
-int g_nj_promo = 0;                             // PAIRALIGN_NJ_PROMO=0|1|2 -> L2 promotion none / 128 B / 256 B (tuning)
-
-int sums_smem() { return g_nj_stages * NJ_TILE * (int)sizeof(float); }
+constexpr int sums_smem() { return NJ_STAGES * NJ_TILE * (int)sizeof(float); }
 
 cudaError_t configure_sums() {                  // > 48 KB of dynamic shared memory needs the opt-in (per device)
-    cudaError_t e = cudaFuncSetAttribute(nj_sums<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * NJ_TILE * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nj_sums<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * NJ_TILE * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nj_sums<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NJ_TILE * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nj_sums<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * NJ_TILE * 4);
-    return e;
+    return cudaFuncSetAttribute(nj_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, sums_smem());
 }
 
 // tensor map of one matrix buffer: boxes of 32 columns x 64 rows
@@ -286,16 +279,13 @@ bool make_tile_map(float *base, int rows, int ld, CUtensorMap *out) {
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * sizeof(float)};
     const cuuint32_t estr[2] = {1, 1}, box[2] = {NJ_W, NJ_TR};
     return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, g_nj_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : g_nj_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 void launch_sums(cudaStream_t st, const SumArgs &a, const CUtensorMap &map) {
     const int span = a.P - (a.lo / NJ_W) * NJ_W;
     const int blocks = (span + NJ_W - 1) / NJ_W;
-    if (g_nj_stages == 3) nj_sums<3><<<blocks, 32, sums_smem(), st>>>(a, map);
-    else if (g_nj_stages == 12) nj_sums<12><<<blocks, 32, sums_smem(), st>>>(a, map);
-    else if (g_nj_stages == 24) nj_sums<24><<<blocks, 32, sums_smem(), st>>>(a, map);
-    else nj_sums<6><<<blocks, 32, sums_smem(), st>>>(a, map);
+    nj_sums<<<blocks, 32, sums_smem(), st>>>(a, map);
 }
 
 // ---- compaction: live slots of [first, P) -> slots [k2, k2 + r) of the other buffer, order kept ------------------
@@ -358,11 +348,6 @@ int pa_nj_build(const float *dist, uint32_t n, pa_nj_join *joins, uint32_t *root
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(PA_ENODEVICE, "no CUDA device available; neighbour joining has no CPU fallback");
-    const char *env = getenv("PAIRALIGN_NJ_STAGES");
-    g_nj_stages = env ? atoi(env) : NJ_STAGES_DEFAULT;
-    if (g_nj_stages != 3 && g_nj_stages != 12 && g_nj_stages != 24) g_nj_stages = NJ_STAGES_DEFAULT;
-    env = getenv("PAIRALIGN_NJ_PROMO");
-    g_nj_promo = env ? atoi(env) : 0;
     const int k0 = epoch_len((int)n);
     const int p_max = (int)n + k0;                                        // < 65536: ranks are p << 16 | q
     const int ld = (p_max + 127) & ~127;                                  // the widest column block is 128

@@ -2,7 +2,7 @@
 """Neighbour joining timing: pa_nj_build on synthetic tree-like matrices, the achieved
 HBM rate against MEASURED_PEAKS.json, and the unmodified reference treeator -n (oracle/_ref) on a bounded size.
 
-    python tools/nj_bench.py [--taxa 1000,2000,5000,10000] [--ref-taxa 1000] [--cols 0]
+    python tools/nj_bench.py [--taxa 1000,2000,5000,10000] [--ref-taxa 1000]
 """
 import argparse
 import json
@@ -43,10 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--taxa", default="1000,2000,5000,10000")
     ap.add_argument("--ref-taxa", type=int, default=1000)
-    ap.add_argument("--cols", type=int, default=0)
     args = ap.parse_args()
-    if args.cols:
-        os.environ["PAIRALIGN_NJ_COLS"] = str(args.cols)
     from phylommand_b200 import capi
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm = peaks.get("hbm_gbs")
