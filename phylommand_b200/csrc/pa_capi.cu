@@ -303,7 +303,8 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
                             (c.force_cta || c.est_long_pairs < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
     // pairs too long for plain 16-bit scores stay on the s16x2 kernel (floating-window variant) unless they go to the
     // CTA kernel; the edge rows then take two bbuf entries each
-    const bool win = duo && c.kduo == 0 && !c.no_win && c.max_len > l16 && !route_long &&
+    // (a gap extension beyond -1024 could wrap a 16-bit half before the maximum with the opening term is taken)
+    const bool win = duo && c.kduo == 0 && !c.no_win && c.max_len > l16 && !route_long && p.gap_ext >= -1024 &&
                      (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;

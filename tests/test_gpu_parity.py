@@ -277,6 +277,14 @@ def test_floating_window_s16x2_long_pairs(gpu, oracle):
     # the int32 one-pair-per-warp kernel (explicit pair list) agrees
     ab = np.array([gpu.pair_from_index(k) for k in range(len(got))])
     assert gpu.align_pairs(ab[:, 0], ab[:, 1]).tobytes() == got.tobytes()
+    # other scoring parameters on the same path (wider gaps between neighbouring states, lower 16-bit limit)
+    for sc in (dict(match=5, mismatch=-4, gap_open=-10, gap_ext=-2), dict(match=20, mismatch=-25, gap_open=-100, gap_ext=-7)):
+        gpu.upload(enc[:6])
+        got = gpu.align_all_pairs(**sc)
+        t = gpu.timing()
+        assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_cta_ms"] == 0.0
+        _same(got, _oracle_all(oracle, enc[:6], threads=12, match=sc["match"], mismatch=sc["mismatch"], go=sc["gap_open"],
+                               ge=sc["gap_ext"]))
 
 
 def test_cta_per_pair_kernel_long_pairs(gpu, oracle):
