@@ -3,10 +3,43 @@
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
+#include <unordered_map>
 
 namespace pab {
 
-MadGroups::MadGroups() : root_(new Node()) {}
+struct MadGroups::NameIndex { std::unordered_map<std::string, int> ids; };
+
+MadGroups::MadGroups() : root_(new Node()), index_(new NameIndex()) {}
+
+int MadGroups::intern(const std::string &s) {
+    auto it = index_->ids.find(s);
+    if (it != index_->ids.end()) return it->second;
+    const int id = (int)index_->ids.size();
+    index_->ids.emplace(s, id);
+    return id;
+}
+
+bool MadGroups::insert_value(int id1, const std::string &s1, int id2, const std::string &s2, float value) {
+    if (id1 < 0 || id2 < 0 || std::isnan(value)) return insert_value(s1, s2, value);
+    const size_t need = (size_t)(id1 > id2 ? id1 : id2) + 1;
+    if (memo_.size() < need) memo_.resize(need);
+    std::vector<Node *> &row = memo_[(size_t)id1];
+    if (row.size() <= (size_t)id2) row.resize((size_t)id2 + 1, nullptr);
+    if (Node *leaf = row[(size_t)id2]) {
+        // find_node_insert_value's last step (src/align_group.cpp:84-91)
+        value *= kPrecision;
+        if (value > kBins - 1) value = kBins - 1;
+        int bin = int(value);
+        if (bin < 0) bin = 0;
+        leaf->hist[bin] += 1;
+        return true;
+    }
+    const unsigned long w0 = warnings_;
+    last_leaf_ = nullptr;
+    const bool ok = insert_value(s1, s2, value);
+    if (ok && warnings_ == w0 && last_leaf_) row[(size_t)id2] = last_leaf_;
+    return ok;
+}
 
 bool MadGroups::insert_value(const std::string &s1, const std::string &s2, float value) {
     // common leading taxa of "a; b; c" strings; the separator is ';' plus ONE skipped
@@ -53,6 +86,7 @@ void MadGroups::find_node_insert_value(std::string taxon, float value, Node *lea
         int bin = int(value);
         if (bin < 0) bin = 0;      // only reachable through -0.0 / rounding; the reference would index below the array
         leaf->hist[bin] += 1;
+        last_leaf_ = leaf;
         return;
     }
     bool found = false;

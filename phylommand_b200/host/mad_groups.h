@@ -19,6 +19,13 @@ public:
     // the two "a; b; c" strings share.  Returns false (and stores nothing) for a NaN,
     // which indexes out of bounds in the reference.
     bool insert_value(const std::string &taxon_string1, const std::string &taxon_string2, float value);
+    // The same with the two strings named by small integers the caller keeps stable (one per distinct string, e.g.
+    // from intern()): the histogram a pair of strings leads to is looked up once and remembered, so the 12 million
+    // inserts of a 5 000-sequence run cost an array access each instead of string splitting and a tree walk.  The
+    // first insert of every (id1, id2) goes through insert_value(), in the caller's order, so nodes are created in
+    // the reference's order; outcomes that print a warning are not remembered (they warn every time).
+    bool insert_value(int id1, const std::string &taxon_string1, int id2, const std::string &taxon_string2, float value);
+    int intern(const std::string &taxon_string);
     // get_levels (src/align_group.cpp:133-166)
     std::string get_levels() const;
     // aprox_mad (src/align_group.h:62-67)
@@ -38,6 +45,10 @@ private:
     std::string get_levels(const Node *leaf) const;
     std::unique_ptr<Node> root_;
     unsigned long warnings_ = 0;
+    Node *last_leaf_ = nullptr;                       // histogram the last successful insert went to
+    std::vector<std::vector<Node *>> memo_;           // [id1][id2] -> histogram node, nullptr = not known
+    struct NameIndex;                                 // string -> id
+    std::shared_ptr<NameIndex> index_;
 };
 
 }  // namespace pab

@@ -185,6 +185,7 @@ public:
         : opt_(o), cut_off_(cut_off), batch_(batch), out_(out) {}
 
     std::function<std::string(const PairView &, int)> taxon_of;   // get_taxon_string of side 1 / 2 (src/seqdatabase.h:106-114)
+    bool taxon_per_sequence = false;   // taxon_of depends on the sequence only: strings and their ids are kept per sequence
     std::function<float(long)> comp_of;                           // get_comp_value(accession or lead) (src/seqdatabase.h:97-105)
     // get_x()/get_y() of the pair being replayed, when a batch of alignments is at hand (mode 'a')
     std::function<bool(const PairView &, std::string &, std::string &)> alignment_of;
@@ -257,6 +258,7 @@ private:
     // src/pairalign.cpp:690-805
     void group(const PairView &v, const PairStats &st) {
         const long a1 = v.cid1, a2 = v.cid2;
+        if (taxon_per_sequence && v.seq2 >= 0) { group_cached(v, st); return; }
         const std::string tax1 = taxon_of(v, 1), tax2 = v.seq2 >= 0 ? taxon_of(v, 2) : std::string();
         if (cut_off_ > 0.000000001 && v.seq2 >= 0) {
             const long c1 = clusters.get_cluster(a1), c2 = clusters.get_cluster(a2);
@@ -276,6 +278,38 @@ private:
             }
         } else {
             deviations.insert_value(tax1, tax2, (float)st.jc_minus_p());
+        }
+    }
+    // group() for the all-pairs loop over one FASTA file: the taxon string of a sequence is fetched once and interned,
+    // so the MAD insert of a pair is an array access (MadGroups::insert_value with ids).  Same decisions, same order.
+    int cached_taxon_id(const PairView &v, int side) {
+        const size_t s = (size_t)(side == 1 ? v.seq1 : v.seq2);
+        if (tax_id_[s] == -2) { tax_cache_[s] = taxon_of(v, side); tax_id_[s] = deviations.intern(tax_cache_[s]); }
+        return tax_id_[s];
+    }
+    void group_cached(const PairView &v, const PairStats &st) {
+        const long a1 = v.cid1, a2 = v.cid2;
+        const size_t need = (size_t)std::max(v.seq1, v.seq2) + 1;      // grow first: the references below must stay valid
+        if (tax_cache_.size() < need) { tax_cache_.resize(need); tax_id_.resize(need, -2); }
+        const int id1 = cached_taxon_id(v, 1), id2 = cached_taxon_id(v, 2);
+        const std::string &tax1 = tax_cache_[(size_t)v.seq1], &tax2 = tax_cache_[(size_t)v.seq2];
+        if (cut_off_ > 0.000000001) {
+            const long c1 = clusters.get_cluster(a1), c2 = clusters.get_cluster(a2);
+            const bool free1 = (c1 == ClusterStore::EMPTY || c1 == ClusterStore::LEAD);
+            const bool free2 = (c2 == ClusterStore::EMPTY || c2 == ClusterStore::LEAD);
+            if (st.similarity() > cut_off_) {
+                const float comp1 = comp_of(free1 ? a1 : c1);
+                const float comp2 = comp_of(free2 ? a2 : c2);
+                if (comp1 >= comp2) absorb(a1, c1, a2, c2, free2);
+                else absorb(a2, c2, a1, c1, free1);
+            } else {
+                if (c1 == ClusterStore::EMPTY) upd(a1, ClusterStore::LEAD, true);
+                if (c2 == ClusterStore::EMPTY) upd(a2, ClusterStore::LEAD, true);
+                if (!tax1.empty() && tax1 != "empty" && !tax2.empty() && tax2 != "empty" && free1 && free2)
+                    deviations.insert_value(id1, tax1, id2, tax2, (float)st.jc_minus_p());
+            }
+        } else {
+            deviations.insert_value(id1, tax1, id2, tax2, (float)st.jc_minus_p());
         }
     }
     // winner w (cluster state cw) takes in loser l (cluster state cl); src/pairalign.cpp:717-775
@@ -298,6 +332,8 @@ private:
     SeqpairBatch &batch_;
     Out &out_;
     unsigned int n_seq_ = 0;
+    std::vector<std::string> tax_cache_;   // taxon string per sequence (taxon_per_sequence)
+    std::vector<int> tax_id_;              // its MadGroups::intern() id, -2: not fetched yet
 };
 
 // cut-off string "gene,value,gene,value" or a bare number (src/pairalign.cpp:456-479)
@@ -426,6 +462,7 @@ void run_fasta(const Options &opt, Out &out) {
             return taxonomy.empty() ? r.taxon : lookup_taxonomy(taxonomy, r.accno);
         };
         rp.comp_of = [&](long s) { return index[(size_t)s].comp_value(); };
+        rp.taxon_per_sequence = true;
         if (opt.matrix && mode == 'd')
             out.put("Proportion different/Similarity/Jukes-Cantor distance/Difference between JC and similarity\n");
         pa_params params{7, -5, -15, -1, opt.aligned ? 1 : 0};      // src/pairalign.cpp:682, src/seqpair.h:57-58
