@@ -65,6 +65,17 @@ def workload(name: str, n_gpus: int, strong: bool = False):
         n = int(round(16 * (n_gpus ** 0.5)))
         names, seqs = synth.make_long(n, 1005)
         label = f"synthetic {n} x 30 kb (seed 1005), all-pairs [profiling size]"
+    elif name == "c2n":
+        # config 2 with two IUPAC ambiguity codes in every sequence: every pair takes the general (4-bit) kernel
+        import numpy as _np
+        n = int(round(1000 * (n_gpus ** 0.5)))
+        names, seqs = synth.make_16s_like(n, 1002)
+        rng = _np.random.default_rng(5)
+        amb = _np.frombuffer(b"RYSWKMN", dtype=_np.uint8)
+        seqs = [s.copy() for s in seqs]
+        for s_ in seqs:
+            s_[rng.integers(1, len(s_), size=2)] = amb[rng.integers(0, len(amb), size=2)]
+        label = f"synthetic {n} x 1.5 kb 16S-like (seed 1002) with 2 IUPAC codes per sequence, all-pairs"
     elif name == "c5w":
         n = int(round(64 * (n_gpus ** 0.5)))
         names, seqs = synth.make_long(n, 1005, length=7600, spread=0.05)
@@ -197,7 +208,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "c5s", "c5w", "tiny"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2n", "c3", "c4", "c5", "c5s", "c5w", "tiny"])
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")

@@ -14,6 +14,9 @@ BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
 _MASK_OF = np.zeros(256, dtype=np.uint8)
 for _ch, _m in zip(b"ACGT", (1, 4, 2, 8)):
     _MASK_OF[_ch] = _m
+# IUPAC ambiguity codes (A=1 G=2 C=4 T=8, reference src/seqpair.cpp:22-60)
+for _ch, _m in zip(b"RYSWKMBDHVN", (1 | 2, 4 | 8, 2 | 4, 1 | 8, 2 | 8, 1 | 4, 2 | 4 | 8, 1 | 2 | 8, 1 | 4 | 8, 1 | 2 | 4, 15)):
+    _MASK_OF[_ch] = _m
 
 
 def _mutate(seq: np.ndarray, divergence: float, rng: np.random.Generator) -> np.ndarray:
@@ -115,7 +118,7 @@ def make_random(n: int, seed: int, lo: int, hi: int, iupac: float = 0.0, gaps: f
 
 
 def to_masks(seq: np.ndarray) -> np.ndarray:
-    """ACGT byte array -> 4-bit sets (only valid for pure A/C/G/T input)."""
+    """Upper-case A/C/G/T/IUPAC byte array -> 4-bit sets (no gaps)."""
     return _MASK_OF[seq]
 
 
