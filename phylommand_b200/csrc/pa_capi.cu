@@ -60,10 +60,13 @@ struct Device {
     size_t deferred_cap = 0;
     unsigned long long *row_items = nullptr;  // items (pairs of pairs) in rows before a; n_seq+1 entries
     size_t cap_row_items = 0, cap_p2 = 0, cap_p4 = 0, cap_off2 = 0, cap_off4 = 0, cap_len = 0, cap_pure = 0, cap_bbuf = 0;
+    uint8_t *fastok = nullptr;                // pure, or sparse ambiguity codes (s16x2 AMB variant)
+    uint32_t *exc = nullptr, *exc_off = nullptr;
+    size_t cap_fastok = 0, cap_exc = 0, cap_exc_off = 0;
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_duo_amb = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -141,6 +144,9 @@ struct Context {
     std::vector<uint8_t> host_pure;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
+    bool all_fast = true;              // every sequence is pure or has only sparse ambiguity codes
+    bool any_sparse = false;           // ... and at least one is of the second kind
+    bool no_amb = false;               // PAIRALIGN_NO_AMB=1: ambiguity codes always take the general kernel (tuning, tests)
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
     int kduo = 0;                      // strip width of the s16x2 kernel; 0: per work item (duo_pick_k)
     int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 forces one width (tuning)
@@ -162,6 +168,7 @@ void free_device(Device &d) {
     if (d.id < 0) return;
     cudaSetDevice(d.id);
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
+    cudaFree(d.fastok); cudaFree(d.exc); cudaFree(d.exc_off);
     cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3); cudaFree(d.bbuf);
     cudaFree(d.row_items);
     if (d.ev_mid) cudaEventDestroy(d.ev_mid);
@@ -179,6 +186,7 @@ void free_device(Device &d) {
 SeqStore store_of(const Device &d, uint32_t n_seq) {
     SeqStore s;
     s.p2 = d.p2; s.p4 = d.p4; s.off2 = d.off2; s.off4 = d.off4; s.len = d.len; s.pure = d.pure; s.n_seq = n_seq;
+    s.fastok = d.fastok; s.exc = d.exc; s.exc_off = d.exc_off;
     return s;
 }
 
@@ -277,7 +285,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const SeqStore S = store_of(d, c.n_seq);
     Scoring sc{p.match, p.mismatch, p.gap_open, p.gap_ext};
     PairSource src{first, d_ia, d_ib, nullptr};
-    CU(cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), d.stream));
+    CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.n_deferred, 0, 3 * sizeof(unsigned int), d.stream));
     d.chunk_duo = d.chunk_fast = d.chunk_cta = d.chunk_gen = false;
     const int threads = WARPS_PER_CTA * 32;
@@ -304,6 +312,8 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     // pairs too long for plain 16-bit scores stay on the s16x2 kernel (floating-window variant) unless they go to the
     // CTA kernel; the edge rows then take two bbuf entries each
     // (a gap extension beyond -1024 could wrap a 16-bit half before the maximum with the opening term is taken)
+    // sequences with sparse IUPAC codes: a second launch of the s16x2 kernel in its AMB form takes their items
+    const bool amb = duo && c.kduo == 0 && c.any_sparse && !c.no_amb;
     const bool win = duo && c.kduo == 0 && !c.no_win && c.max_len > l16 && !route_long && p.gap_ext >= -1024 &&
                      (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
     int rc = ensure_deferred(d, (size_t)count);
@@ -317,7 +327,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         if (c.kduo == 0)
             pa_warp_duo_kernel<0><<<d.grid_duo_auto, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
-                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0);
+                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, amb ? 1 : 0);
         else if (c.kduo == 8)
             pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
@@ -332,8 +342,15 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
                 d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
+        if (amb) {   // the items with sparse ambiguity codes: same work items, AMB variant (its own work counter)
+            pa_warp_duo_kernel<-1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
+            CU(cudaGetLastError());
+            d.launches += 1;
+        }
         d.chunk_duo = true;
-        stage2 = !c.all_pure || (c.max_len > l16 && !win);       // something may have been deferred
+        stage2 = !(amb ? c.all_fast : c.all_pure) || (c.max_len > l16 && !win);       // something may have been deferred
         src2.idx = d.deferred;
         count2 = d.n_deferred;
     } else if (fast) {
@@ -512,7 +529,7 @@ int pa_init(const int *devices, int n_dev) {
         for (auto &ev : d.ev_done) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
         if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_mid);
         if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_cta);
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 4 * sizeof(unsigned long long));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 5 * sizeof(unsigned long long));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
         int occ = 0;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
@@ -523,6 +540,8 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_duo8 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
         d.grid_duo_auto = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<-1>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo_amb = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
@@ -531,7 +550,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_amb), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -545,6 +564,7 @@ int pa_init(const int *devices, int n_dev) {
     if (const char *f = std::getenv("PAIRALIGN_KDUO_A")) c->kduo_step_cost = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_NO_CTA")) c->no_cta = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_NO_WIN")) c->no_win = (f[0] == '1');
+    if (const char *f = std::getenv("PAIRALIGN_NO_AMB")) c->no_amb = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_DUO_MINB")) c->duo_minb = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_FORCE_CTA")) c->force_cta = (f[0] == '1');
     g_ctx = c;
@@ -610,7 +630,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     if (!offsets || (!masks && n_seq && offsets[n_seq] > 0)) return fail(PA_EINVAL, "NULL sequence buffer");
     Context &c = *g_ctx;
     std::vector<uint32_t> len(n_seq), off2(n_seq), off4(n_seq);
-    std::vector<uint8_t> pure(n_seq);
+    std::vector<uint8_t> pure(n_seq), fastok(n_seq);
+    std::vector<uint32_t> exc, exc_off((size_t)n_seq + 1, 0);
+    bool all_fast = true;
     uint64_t w2 = 0, w4 = 0;
     uint32_t max_len = 0;
     bool all_pure = true;
@@ -638,7 +660,34 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         }
         pure[s] = pr ? 1 : 0;
         all_pure = all_pure && pr;
+        // Sparse ambiguity codes (s16x2 AMB variant): no gap character, positions 1..15 plain, ranges of DIFFERENT sets at
+        // least 16 plain bases apart, at most EXC_MAX ranges (a range = up to 255 equal sets in a row)
+        exc_off[s] = (uint32_t)exc.size();
+        bool ok = true;
+        if (!pr) {
+            const size_t first_range = exc.size();
+            int last_end = -1000;           // end (exclusive) of the previous range
+            uint32_t last_set = 0;
+            for (uint32_t k = 0; k < len[s] && ok; ) {
+                const uint32_t v = src[k] & 15u;
+                if (v == 0) { ok = false; break; }
+                if (v == 1 || v == 2 || v == 4 || v == 8) { ++k; continue; }
+                uint32_t run = 1;
+                while (k + run < len[s] && (src[k + run] & 15u) == v && run < 255) ++run;
+                if (k >= 1 && k <= 15) ok = false;
+                if (k == 0 && run > 1) ok = false;
+                if (last_set != v && (int)k - last_end < 16) ok = false;
+                exc.push_back(k | (run << 16) | (v << 24));
+                last_end = (int)(k + run); last_set = v;
+                k += run;
+            }
+            if (exc.size() - first_range > (size_t)EXC_MAX) ok = false;
+            if (!ok) exc.resize(first_range);
+        }
+        fastok[s] = ok ? 1 : 0;
+        all_fast = all_fast && ok;
     }
+    exc_off[n_seq] = (uint32_t)exc.size();
     c.n_seq = n_seq;
     c.host_masks.assign(masks, masks + offsets[n_seq]);
     c.host_offsets.assign(offsets, offsets + n_seq + 1);
@@ -646,6 +695,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.len = len;
     c.max_len = max_len;
     c.all_pure = all_pure;
+    c.all_fast = all_fast;
+    c.any_sparse = false;
+    for (uint32_t s = 0; s < n_seq; ++s) c.any_sparse = c.any_sparse || (fastok[s] && !pure[s]);
     c.tri.build(len.data(), n_seq);
     {
         uint64_t n_long = 0;
@@ -681,6 +733,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
         CU(grow((void **)&d.len, d.cap_len, nidx * 4));
         CU(grow((void **)&d.pure, d.cap_pure, nidx));
+        CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
+        CU(grow((void **)&d.exc, d.cap_exc, std::max<size_t>(exc.size(), 1) * 4));
+        CU(grow((void **)&d.exc_off, d.cap_exc_off, (nidx + 1) * 4));
         d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
         if (max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
         CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
@@ -692,6 +747,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
             CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
             CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
             CU(cudaMemcpyAsync(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.fastok, fastok.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.exc_off, exc_off.data(), ((size_t)n_seq + 1) * 4, cudaMemcpyHostToDevice, d.stream));
+            if (!exc.empty()) CU(cudaMemcpyAsync(d.exc, exc.data(), exc.size() * 4, cudaMemcpyHostToDevice, d.stream));
         }
     }
     for (auto &d : c.dev) {       // the host vectors above die at return
@@ -914,7 +972,7 @@ int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32
         CU(cudaMemcpyAsync(d.d_ib, ib + s0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_dirs_off, h_dirs_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_ops_off, h_ops_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
-        CU(cudaMemsetAsync(d.counters, 0, 4 * sizeof(unsigned long long), d.stream));
+        CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
         CU(cudaMemsetAsync(d.d_res, 0, nb * sizeof(pa_pair_result), d.stream));
         if (any_pure) {
             pa_warp32_dirs_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters, d.bbuf, d.bbuf_rows,
