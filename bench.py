@@ -45,7 +45,21 @@ def workload(name: str, n_gpus: int, strong: bool = False):
     from phylommand_b200 import synth
     if strong:                      # fixed set: the triangle is cut into n_gpus ranges
         n_gpus = 1
-    if name == "c2":
+    if name == "c1":
+        # BASELINE.json configs[0]: the reference's example file, gap characters removed (the DP path); 103 sequences,
+        # 12 of them with IUPAC codes.  Fixed size (no weak scaling); the CPU baseline runs the whole file.
+        import numpy as _np
+        names, seqs, cur = [], [], None
+        for line in (ROOT / "tests" / "golden" / "example_files" / "alignment_file_degapped.fst").read_text().split("\n"):
+            if line.startswith(">"):
+                names.append(line[1:].split("|")[0].replace(" ", "")); seqs.append("")
+            elif names:
+                seqs[-1] += line.strip()
+        order = sorted(range(len(names)), key=lambda k: names[k].encode())     # the reference's std::map order
+        names = [names[k] for k in order]
+        seqs = [_np.frombuffer(seqs[k][1:].upper().encode(), dtype=_np.uint8) for k in order]   # first character dropped
+        label = f"example_files/alignment_file.fst without gap characters ({len(seqs)} sequences), all-pairs"
+    elif name == "c2":
         n = int(round(1000 * (n_gpus ** 0.5)))
         names, seqs = synth.make_16s_like(n, 1002)
         label = f"synthetic {n} x 1.5 kb 16S-like (seed 1002), all-pairs"
@@ -183,7 +197,7 @@ def run_reference(args, rank: int, world: int) -> None:
         return
     names, seqs, label = workload(args.workload, args.gpus, args.scaling == "strong")
     threads = min(host_threads(), 64)
-    k = args.cpu_prefix or cpu_prefix_for(threads)
+    k = args.cpu_prefix or (len(seqs) if args.workload == "c1" else cpu_prefix_for(threads))
     times = []
     res = None
     for it in range(args.warmup + args.steps):
@@ -208,7 +222,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2n", "c3", "c4", "c5", "c5s", "c5w", "tiny"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2n", "c3", "c4", "c5", "c5s", "c5w", "tiny"])
     ap.add_argument("--cpu-prefix", type=int, default=0, help="sequences in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
@@ -326,7 +340,7 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "gcups": total_cells / (el / args.steps) / 1e9,
+            "data": "reference example file" if args.workload == "c1" else "synthetic", "gcups": total_cells / (el / args.steps) / 1e9,
             "config": {"workload": label, "mode": "-j -m (Jukes-Cantor matrix inputs: score, mismatches, columns per pair)",
                        "pairs": total_pairs, "cells": total_cells, "scoring": "match 7 / mismatch -5 / gap open -15 / extend -1",
                        "sharding": f"triangle cut into {world} contiguous ranges balanced by DP cells, no collective",
@@ -364,7 +378,7 @@ def main() -> None:
             }
         if not args.no_cpu_baseline:
             threads = min(host_threads(), 64)
-            k = args.cpu_prefix or cpu_prefix_for(threads)
+            k = args.cpu_prefix or (len(seqs) if args.workload == "c1" else cpu_prefix_for(threads))
             cb = cpu_reference_run(names, seqs, k, threads)
             line["cpu_baseline"] = {"value": cb["pairs"] / cb["seconds"], "unit": "pairs/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"], "gcups": cb["cells"] / cb["seconds"] / 1e9, "seconds": cb["seconds"]}
