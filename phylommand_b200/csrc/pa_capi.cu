@@ -699,11 +699,6 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.any_sparse = false;
     for (uint32_t s = 0; s < n_seq; ++s) c.any_sparse = c.any_sparse || (fastok[s] && !pure[s]);
     c.tri.build(len.data(), n_seq);
-    {
-        uint64_t n_long = 0;
-        for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
-        c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
-    }
     // strip width of the s16x2 kernel: chosen per work item inside the kernel (0); PAIRALIGN_KDUO=8|12 forces one width
     c.kduo = (c.kduo_forced == 8 || c.kduo_forced == 12) ? c.kduo_forced : 0;
     {
