@@ -83,6 +83,7 @@ typedef struct {
     double   dp_general_ms;  /* the IUPAC/gap (int32 wrap) kernel alone                    */
     double   dp_duo_ms;      /* the s16x2 kernel (two pairs per warp); with -A: the stats kernel */
     double   dp_cta_ms;      /* the CTA-per-pair kernel for long pairs                       */
+    double   walk_ms;        /* pa_align_pairs_ops: the walk back over the stored moves (in kernel_ms) */
 } pa_timing;
 
 /* ---- life cycle --------------------------------------------------------- */

@@ -29,7 +29,8 @@ class PaTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("total_ms", C.c_double), ("cells", C.c_uint64), ("pairs", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("n_devices", C.c_uint32),
-                ("dp_fast_ms", C.c_double), ("dp_general_ms", C.c_double), ("dp_duo_ms", C.c_double), ("dp_cta_ms", C.c_double)]
+                ("dp_fast_ms", C.c_double), ("dp_general_ms", C.c_double), ("dp_duo_ms", C.c_double), ("dp_cta_ms", C.c_double),
+                ("walk_ms", C.c_double)]
 
 
 #: every symbol include/pairalign_b200.h declares: name -> (restype, argtypes)

@@ -886,59 +886,58 @@ static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool pure, bool fast) {
     return (bytes + 127) / 128 * 128;
 }
 
-int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
-                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
-    int rc = check_params(params);
-    if (rc) return rc;
-    if (count == 0) return PA_OK;
-    if (!ia || !ib || !ops || !op_offsets || !n_ops) return fail(PA_EINVAL, "NULL buffer");
-    Context &c = *g_ctx;
-    if (!c.dev[0].p4) return fail(PA_EINVAL, "no sequences uploaded");
-    if (params->aligned) return fail(PA_EINVAL, "pairalign -A prints its input: there is nothing to trace back");
-    Device &d = c.dev[0];
+// pairalign -a on one device: pairs [lo, hi) of the caller's list in batches sized to the move store.
+// Long A/C/G/T pairs take a CTA each (pa_cta32_kernel<KFAST, true>) when a batch holds too few of them to keep a
+// one-pair-per-warp kernel busy -- which the size of their move stores (2 bits per cell: 226 MB for 30 kb x 30 kb)
+// all but guarantees.
+static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t *ia, const uint32_t *ib, uint64_t lo, uint64_t hi,
+                     uint8_t *ops, const uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res, double *kernel_ms) {
+    if (lo >= hi) return PA_OK;
     CU(cudaSetDevice(d.id));
-    const bool fast = fast_params_ok(*params);
-    uint64_t total_ops = 0;
-    for (uint64_t k = 0; k < count; ++k) {
-        if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
-        op_offsets[k] = total_ops;
-        total_ops += (uint64_t)c.len[ia[k]] + c.len[ib[k]];
-    }
-    op_offsets[count] = total_ops;
-    if (total_ops > ops_cap) return fail(PA_EINVAL, "op buffer holds %llu bytes, %llu needed (sum of both lengths over the pairs)",
-                                         (unsigned long long)ops_cap, (unsigned long long)total_ops);
+    const bool fast = fast_params_ok(prm);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget = std::min<uint64_t>((uint64_t)((free_b + d.cap_dirs) / 2), 48ull << 30);
-    const Scoring sc{params->match, params->mismatch, params->gap_open, params->gap_ext};
+    const uint64_t budget = std::min<uint64_t>((uint64_t)((free_b + d.cap_dirs) / 2), 72ull << 30);
+    const Scoring sc{prm.match, prm.mismatch, prm.gap_open, prm.gap_ext};
     const SeqStore S = store_of(d, c.n_seq);
     const int threads = WARPS_PER_CTA * 32;
     std::vector<unsigned long long> h_dirs_off, h_ops_off;
-    uint64_t s0 = 0;
-    while (s0 < count) {
+    std::vector<uint32_t> h_long;
+    uint64_t s0 = lo;
+    while (s0 < hi) {
         // one batch: as many pairs as the move store holds
         uint64_t e0 = s0, dbytes = 0, obytes = 0;
+        uint64_t ck_e0 = s0, ck_dbytes = 0, ck_obytes = 0;      // the batch as it was after the last whole wave of long pairs
         bool any_pure = false, any_general = false;
-        h_dirs_off.clear(); h_ops_off.clear();
-        while (e0 < count && e0 - s0 < (1ull << 20)) {
+        h_dirs_off.clear(); h_ops_off.clear(); h_long.clear();
+        while (e0 < hi && e0 - s0 < (1ull << 20)) {
             const uint32_t a = ia[e0], b = ib[e0];
             const bool pure = c.host_pure[a] && c.host_pure[b];
             const uint64_t need = (c.len[a] && c.len[b]) ? dirs_bytes(c.len[a], c.len[b], pure, fast) : 0;
             if (dbytes + need > budget) {
                 if (e0 == s0) return fail(PA_ENOMEM, "the moves of pair %llu need %llu bytes; %llu available", (unsigned long long)e0,
                                           (unsigned long long)need, (unsigned long long)budget);
+                // a batch of long pairs runs one pair per CTA: end it on a whole number of waves of the persistent grid
+                if (h_long.size() == e0 - s0 && ck_e0 > s0 && !c.no_cta) {
+                    e0 = ck_e0; dbytes = ck_dbytes; obytes = ck_obytes;
+                    h_dirs_off.resize(e0 - s0); h_ops_off.resize(e0 - s0); h_long.resize(e0 - s0);
+                }
                 break;
             }
             h_dirs_off.push_back(dbytes);
             h_ops_off.push_back(obytes);
             dbytes += need;
             obytes += (uint64_t)c.len[a] + c.len[b];
-            if (pure && fast) any_pure = true; else any_general = true;
+            if (pure && fast) {
+                any_pure = true;
+                if (need && std::max(c.len[a], c.len[b]) > LONG_LEN) h_long.push_back((uint32_t)(e0 - s0));
+            } else any_general = true;
             ++e0;
+            if (h_long.size() == e0 - s0 && h_long.size() % (size_t)d.grid_cta == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
         }
         const uint64_t nb = e0 - s0;
+        const bool route_long = !h_long.empty() && !c.no_cta &&
+                                (c.force_cta || h_long.size() < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
         auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
             if (bytes <= cap && *ptr) return cudaSuccess;
             cudaFree(*ptr); *ptr = nullptr; cap = 0;
@@ -969,27 +968,123 @@ int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32
         CU(cudaMemcpyAsync(d.d_ops_off, h_ops_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
         CU(cudaMemsetAsync(d.d_res, 0, nb * sizeof(pa_pair_result), d.stream));
-        if (any_pure) {
+        if (route_long) {
+            int rc = ensure_deferred(d, (size_t)nb);
+            if (rc) return rc;
+            const unsigned int n_long = (unsigned int)h_long.size();
+            CU(cudaMemcpyAsync(d.deferred3, h_long.data(), h_long.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.n_deferred + 2, &n_long, sizeof n_long, cudaMemcpyHostToDevice, d.stream));
+        }
+        CU(cudaEventRecord(d.ev[0], d.stream));
+        if (any_pure && !(route_long && h_long.size() == nb)) {
             pa_warp32_dirs_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters, d.bbuf, d.bbuf_rows,
-                                                                                d.d_res, d.d_dirs, d.d_dirs_off);
+                                                                                d.d_res, d.d_dirs, d.d_dirs_off,
+                                                                                route_long ? LONG_LEN : 0xffffffffu);
             CU(cudaGetLastError());
+            d.launches += 1;
+        }
+        if (route_long) {
+            PairSource src;
+            src.first = 0; src.ia = d.d_ia; src.ib = d.d_ib; src.idx = d.deferred3;
+            pa_cta32_kernel<KFAST, true><<<d.grid_cta, CTA_WARPS * 32, 0, d.stream>>>(
+                S, sc, src, d.n_deferred + 2, d.counters + 3, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            CU(cudaGetLastError());
+            d.launches += 1;
         }
         if (any_general) {
             pa_general_dirs_kernel<<<d.grid_gen, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters + 1, d.bbuf, d.bbuf_rows,
                                                                          d.d_res, d.d_dirs, d.d_dirs_off, fast ? 0 : 1);
             CU(cudaGetLastError());
+            d.launches += 1;
         }
-        pa_walk_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
-                                                                          d.d_ops_off, d.d_nops, fast ? KFAST : KGEN, KGEN);
+        CU(cudaEventRecord(d.ev[1], d.stream));
+        pa_walk_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
+                                                                        d.d_ops_off, d.d_nops, fast ? KFAST : KGEN, KGEN);
         CU(cudaGetLastError());
+        d.launches += 1;
+        CU(cudaEventRecord(d.ev[2], d.stream));
         CU(cudaMemcpyAsync(ops + op_offsets[s0], d.d_ops, obytes, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaMemcpyAsync(n_ops + s0, d.d_nops, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
         if (res) CU(cudaMemcpyAsync(res + s0, d.d_res, nb * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
+        float dp_ms = 0, walk_ms = 0;
+        CU(cudaEventElapsedTime(&dp_ms, d.ev[0], d.ev[1]));
+        CU(cudaEventElapsedTime(&walk_ms, d.ev[1], d.ev[2]));
+        kernel_ms[0] += dp_ms; kernel_ms[1] += walk_ms;
+        if (route_long) d.cta_ms += dp_ms; else d.fast_ms += dp_ms;
         // the walk wrote each op string backwards (the reference reverses at src/seqpair.cpp:183-188)
         for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);
         s0 = e0;
     }
+    return PA_OK;
+}
+
+int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
+                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (count == 0) return PA_OK;
+    if (!ia || !ib || !ops || !op_offsets || !n_ops) return fail(PA_EINVAL, "NULL buffer");
+    Context &c = *g_ctx;
+    if (!c.dev[0].p4) return fail(PA_EINVAL, "no sequences uploaded");
+    if (params->aligned) return fail(PA_EINVAL, "pairalign -A prints its input: there is nothing to trace back");
+    uint64_t total_ops = 0;
+    unsigned __int128 total_cells = 0;
+    for (uint64_t k = 0; k < count; ++k) {
+        if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
+        op_offsets[k] = total_ops;
+        total_ops += (uint64_t)c.len[ia[k]] + c.len[ib[k]];
+        total_cells += (unsigned __int128)c.len[ia[k]] * c.len[ib[k]];
+    }
+    op_offsets[count] = total_ops;
+    if (total_ops > ops_cap) return fail(PA_EINVAL, "op buffer holds %llu bytes, %llu needed (sum of both lengths over the pairs)",
+                                         (unsigned long long)ops_cap, (unsigned long long)total_ops);
+    // contiguous ranges of the list with nearly equal DP cells, one per device (each on its own host thread);
+    // every range writes its own slice of ops / n_ops / res, so nothing is shared
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t nd = c.dev.size();
+    std::vector<uint64_t> bounds(nd + 1, count);
+    bounds[0] = 0;
+    if (nd > 1) {
+        unsigned __int128 acc = 0;
+        size_t p = 1;
+        for (uint64_t k = 0; k < count && p < nd; ++k) {
+            while (p < nd && acc >= total_cells * p / nd) bounds[p++] = k;
+            acc += (unsigned __int128)c.len[ia[k]] * c.len[ib[k]];
+        }
+    }
+    std::vector<int> rcs(nd, PA_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<double> kms(2 * nd, 0.0);
+    for (auto &d : c.dev) { d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
+    auto work = [&](size_t p) {
+        rcs[p] = ops_range(c, c.dev[p], *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p]);
+        if (rcs[p]) errs[p] = g_err;
+    };
+    if (nd == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t p = 0; p < nd; ++p) th.emplace_back(work, p);
+        for (auto &t : th) t.join();
+    }
+    for (size_t p = 0; p < nd; ++p) if (rcs[p]) { g_err = errs[p]; return rcs[p]; }
+    const auto t1 = std::chrono::steady_clock::now();
+    pa_timing &tm = c.timing;
+    tm = pa_timing();
+    for (size_t p = 0; p < nd; ++p) {
+        const Device &d = c.dev[p];
+        tm.kernel_ms = std::max(tm.kernel_ms, kms[2 * p] + kms[2 * p + 1]);
+        tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
+        tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
+        tm.walk_ms = std::max(tm.walk_ms, kms[2 * p + 1]);
+        tm.kernel_launches += d.launches;
+    }
+    tm.total_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    tm.pairs = count;
+    tm.n_devices = (uint32_t)nd;
+    tm.cells = (uint64_t)total_cells;
     return PA_OK;
 }
 

@@ -331,10 +331,12 @@ pa_warp32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const
 // gedge_all: per CTA one column of n rows for the wrap-around edge plus the
 // virtual row.
 // ---------------------------------------------------------------------------
-template <int K>
+// DIRS (pairalign -a): every block also stores its moves at dirs + dirs_off[e] (layout: see pa_warp32_dirs_kernel).
+template <int K, bool DIRS = false>
 __global__ void __launch_bounds__(CTA_WARPS * 32, 1)
 pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const unsigned int *n_items,
-                unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows, pa_pair_result *out) {
+                unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows, pa_pair_result *out,
+                uint8_t *dirs = nullptr, const unsigned long long *dirs_off = nullptr) {
     __shared__ __align__(16) uint32_t xstage[XSTAGE_WORDS];
     __shared__ __align__(16) int4 rings[CTA_WARPS - 1][RING_ROWS];
     __shared__ int4 tab[8];
@@ -397,7 +399,11 @@ pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const 
                 if (w == CTA_WARPS - 1) edge.out_global = gedge;
                 else { edge.out_ring = rings[w]; edge.out_cons = &cons[w]; }
             }
-            block32<K>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best);
+            if (DIRS)
+                block32<K, RingEdge, true>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best,
+                                           reinterpret_cast<uint32_t *>(dirs + dirs_off[e]) + p * 32 + lane, (uint32_t)P * 32u);
+            else
+                block32<K>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best);
         }
         // combine: last row (lowest column wins ties), last column (from the warp that ran the last block)
         if (lane == 0) { bestRow[w] = best.rowBest; bestJ[w] = best.rowJ; bestRowC[w] = best.rowC; }
@@ -429,7 +435,7 @@ template <int K>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
                       unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
-                      pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off) {
+                      pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off, const uint32_t long_len) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
     __shared__ int4 tabs[WARPS_PER_CTA][8];
     const int lane = threadIdx.x & 31;
@@ -446,6 +452,7 @@ pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, co
         const uint32_t a = ia[e], b = ib[e];
         const int n = (int)S.len[a], m = (int)S.len[b];
         if (n == 0 || m == 0 || !(S.pure[a] && S.pure[b])) continue;
+        if ((uint32_t)max(n, m) > long_len) continue;          // the CTA-per-pair kernel has it (pa_cta32_kernel<K, true>)
         __syncwarp();
         const uint32_t *xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
         const uint32_t *ys = stage_seq(S.p2 + S.off2[b], (uint32_t)(m + 15) >> 4, stage[wib][1], lane);
@@ -473,24 +480,38 @@ pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, co
     }
 }
 
-// One thread per pair: the reference's walk (src/seqpair.cpp:146-178).  ops receives one byte per aligned
+// One warp per pair: the reference's walk (src/seqpair.cpp:146-178).  ops receives one byte per aligned
 // column in the REVERSE order the reference builds them in (it reverses at :183-188; the host does that):
 // 0 = x[i] over y[j], 1 = x[i] over a gap, 2 = gap over y[j].  kcols: strip width of the kernel that wrote the
 // moves of this pair (16 for A/C/G/T pairs, 8 for the general kernel).
+//
+// The walk is a chain of dependent loads, one row of the move store (a different cache line) per step, and the
+// store of a long pair (226 MB for 30 kb x 30 kb) is in DRAM by the time the walk starts.  Lane 0 walks; every
+// WALK_EPOCH rows all lanes prefetch the lines the path will most likely touch WALK_EPOCH..2*WALK_EPOCH rows
+// further up (the diagonal through the current cell, one line either side of it) into L2, so most steps of the
+// chain wait for L2 instead of DRAM.  The prefetch is a hint: a path that leaves the diagonal is still walked
+// exactly, only slower.
+constexpr int WALK_EPOCH = 64;
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __global__ void pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
                                const pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
                                uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
                                const int k_pure, const int k_general) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= count) return;
     const uint32_t a = ia[e], b = ib[e];
     const int n = (int)S.len[a], m = (int)S.len[b];
     uint8_t *o = ops + ops_off[e];
     uint32_t k = 0;
     if (n == 0 || m == 0) {       // nothing to align (undefined in the reference): the other sequence against gaps
-        for (int q = 0; q < n; ++q) o[k++] = 1;
-        for (int q = 0; q < m; ++q) o[k++] = 2;
-        n_ops[e] = k;
+        if (lane == 0) {
+            for (int q = 0; q < n; ++q) o[k++] = 1;
+            for (int q = 0; q < m; ++q) o[k++] = 2;
+            n_ops[e] = k;
+        }
         return;
     }
     const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : k_general);
@@ -499,19 +520,45 @@ __global__ void pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint3
     const size_t stride = (size_t)P * W / 4;
     const uint8_t *d = dirs + dirs_off[e];
     int i = res[e].end_i, j = res[e].end_j;
-    if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
-    else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
-    while (i >= 0 || j >= 0) {
-        uint32_t mv = 3;
-        if (i >= 0 && j >= 0) {
-            const int slot = j + padL;
-            mv = (d[(size_t)i * stride + (slot >> 2)] >> ((slot & 3) * 2)) & 3u;
+    auto prefetch_rows = [&](int i_top) {      // rows i_top, i_top-1, ...: two per lane, along the diagonal through (i, j)
+#pragma unroll
+        for (int h = 0; h < WALK_EPOCH / 32; ++h) {
+            const int r = i_top - lane - 32 * h;
+            const int slot = j - (i - r) + padL;
+            if (r >= 0 && slot >= -128) {
+                const int lo = max(slot - 128, 0), hi = min(max(slot + 128, 0), P * W - 1);
+                const uint8_t *row = d + (size_t)r * stride;
+                prefetch_l2(row + (lo >> 2));
+                if ((hi >> 9) != (lo >> 9)) prefetch_l2(row + (hi >> 2));
+            }
         }
-        if (mv == 0) { o[k++] = 0; --i; --j; }
-        else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
-        else { o[k++] = 2; --j; }
+    };
+    prefetch_rows(i);
+    if (lane == 0) {
+        if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
+        else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
     }
-    n_ops[e] = k;
+    for (;;) {
+        i = __shfl_sync(FULL_MASK, i, 0);
+        j = __shfl_sync(FULL_MASK, j, 0);
+        if (i < 0 && j < 0) break;
+        prefetch_rows(i - WALK_EPOCH);
+        if (lane == 0) {
+            const int i_stop = i - WALK_EPOCH;         // walk until WALK_EPOCH rows are behind us (or the end)
+            while ((i >= 0 || j >= 0) && i > i_stop) {
+                uint32_t mv = 3;
+                if (i >= 0 && j >= 0) {
+                    const int slot = j + padL;
+                    mv = (__ldcg(&d[(size_t)i * stride + (slot >> 2)]) >> ((slot & 3) * 2)) & 3u;
+                }
+                if (mv == 0) { o[k++] = 0; --i; --j; }
+                else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
+                else { o[k++] = 2; --j; }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) n_ops[e] = k;
 }
 
 }  // namespace pa

@@ -490,7 +490,9 @@ void run_fasta(const Options &opt, Out &out) {
             uint32_t max_len = 1;
             for (size_t s = 0; s < N; ++s) max_len = std::max(max_len, batch.length(s));
             const bool want_ops = (mode == 'a' && !opt.aligned);
-            const uint64_t chunk_pairs = want_ops ? std::max<uint64_t>(1, std::min<uint64_t>(kChunkPairs, (256ull << 20) / (2ull * max_len)))
+            // op strings of one batch: 256 MB per device in use (every device takes a contiguous share of the batch)
+            const uint64_t op_bytes = (256ull << 20) * (uint64_t)std::max(1, pa_device_count());
+            const uint64_t chunk_pairs = want_ops ? std::max<uint64_t>(1, std::min<uint64_t>(kChunkPairs, op_bytes / (2ull * max_len)))
                                                   : kChunkPairs;
             size_t cur_k = 0;
             int cur_slot = 0;

@@ -419,3 +419,58 @@ def test_batched_alignments(gpu, oracle):
         assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
         ax, ay = _render(ops[int(off[k]):int(off[k]) + int(n_ops[k])], enc[ia[k]], enc[ib[k]])
         assert ax == wx.tolist() and ay == wy.tolist(), (ia[k], ib[k])
+
+
+def test_batched_alignments_long_pairs_take_a_cta(gpu, oracle):
+    """pairalign -a for pairs longer than 8192: pa_cta32_kernel<16, true> (eight warps per pair, moves stored by
+    every block) next to the one-pair-per-warp kernel for the shorter pairs of the same batch, walked back by
+    the warp-per-pair walk kernel; against the reference-literal traceback of the oracle."""
+    _, seqs = synth.make_long(3, 801, length=9400, spread=0.1)
+    enc = [synth.to_masks(s) for s in seqs]
+    enc.append(enc[1][:300].copy())                  # one-block y against a long x, and the other way round
+    enc.append(enc[2][:8193].copy())                 # just above the threshold, odd length
+    _, short = synth.make_random(2, 802, 200, 900)
+    enc += [synth.to_masks(s) for s in short]        # stay on the warp kernel
+    gpu.upload(enc)
+    ia = np.array([0, 1, 3, 0, 4, 5, 2, 6])
+    ib = np.array([1, 0, 0, 3, 2, 6, 4, 5])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    t = gpu.timing()
+    assert t["dp_cta_ms"] > 0 and t["walk_ms"] > 0 and t["kernel_launches"] == 3
+    stats = gpu.align_pairs(ia, ib)
+    assert res.tobytes() == stats.tobytes()
+    for k in range(len(ia)):
+        r, wx, wy = oracle.align_full(enc[ia[k]], enc[ib[k]])
+        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
+        ax, ay = _render(ops[int(off[k]):int(off[k]) + int(n_ops[k])], enc[ia[k]], enc[ib[k]])
+        assert ax == wx.tolist() and ay == wy.tolist(), (ia[k], ib[k])
+
+
+def test_alignments_at_config5_size_are_consistent(gpu):
+    """BASELINE.json config 5 sizes (30 kb pairs), where the oracle's full matrices do not fit: the op strings must
+    consume both sequences exactly, and recounting compared / differing columns along them must give the (dist, len)
+    of the record -- which in turn must equal what the statistics-only s16x2 floating-window kernel carried forward."""
+    _, seqs = synth.make_long(6, 1005, length=30000, spread=0.05)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    n = len(enc)
+    ia = np.array([a for a in range(n) for b in range(a + 1, n)])
+    ib = np.array([b for a in range(n) for b in range(a + 1, n)])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    assert gpu.timing()["dp_cta_ms"] > 0
+    stats = gpu.align_all_pairs()
+    assert res.tobytes() == stats.tobytes()
+    for k in range(len(ia)):
+        o = ops[int(off[k]):int(off[k]) + int(n_ops[k])]
+        x, y = enc[ia[k]], enc[ib[k]]
+        assert int((o != 2).sum()) == len(x) and int((o != 1).sum()) == len(y)
+        xi = np.cumsum(o != 2) - 1
+        yj = np.cumsum(o != 1) - 1
+        both = o == 0
+        assert int(both.sum()) == int(res[k]["len"])
+        assert int(((x[xi[both]] & y[yj[both]]) == 0).sum()) == int(res[k]["dist"])
+        # the walk starts at the end cell: no compared column lies beyond it
+        last = int(np.flatnonzero(both)[-1])
+        assert xi[last] <= int(res[k]["end_i"]) and yj[last] <= int(res[k]["end_j"])
