@@ -161,6 +161,7 @@ public:
         maybe_flush();
     }
     void raw(const char *p, size_t n) { buf_.append(p, n); maybe_flush(); }
+    void fill(char c, size_t n) { buf_.append(n, c); maybe_flush(); }
     void flush() {
         if (!buf_.empty()) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); }
         std::fflush(stdout);
@@ -168,6 +169,61 @@ public:
 private:
     void maybe_flush() { if (buf_.size() > (1u << 20)) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); } }
     std::string buf_;
+};
+
+// ---- the text of one pair in the statistic modes (src/pairalign.cpp:815-851) -----------
+// Depends on the pair alone: its two names, its place in the triangle and its (mismatches, columns) record.
+// Measured on the 16-core GPU host: 43 M values/s on one thread (49 995 000 values of a 10 000-sequence -A -j -n -m run in
+// 1.17 s, the reader of the pipe being the limit); formatting batches on several threads was tried and is not faster.
+class TextEmitter {
+public:
+    TextEmitter(char mode, bool matrix, bool names) : mode_(mode), matrix_(matrix), names_(names) {}
+    static bool handles(char mode) { return mode == 'd' || mode == 'c' || mode == 'j' || mode == 'p' || mode == 's'; }
+
+    // src/pairalign.cpp:594-602; row = number of rows begun before this one
+    template <class Sink>
+    void begin_row(Sink &out, const std::string &accno1, unsigned int row) const {
+        if (row > 0) out.put('\n');
+        if (names_) { out.put(accno1); out.put(' '); }
+        if (row > 0) out.fill(' ', row);
+    }
+    template <class Sink>
+    void pair(Sink &out, const std::string &accno1, const std::string &accno2, const PairStats &st) {
+        if (mode_ == 'd') {
+            if (!matrix_) {
+                names(out, accno1, accno2);
+                out.put("Proportion sites that are different (and similarity): ");
+                out.num(st.proportion_different()); out.put(" ("); out.num(st.similarity());
+                out.put("), Jukes-Cantor distance: "); out.num(st.jc_distance());
+                out.put(", difference between the two: "); out.num(st.jc_minus_p()); out.put(".\n");
+            } else {
+                out.num(st.proportion_different()); out.put('/'); out.num(st.similarity()); out.put('/');
+                out.num(st.jc_distance()); out.put('/'); out.num(st.jc_minus_p()); out.put('.');
+            }
+            return;
+        }
+        // The printed figure depends on (mismatches, columns) only, and an all-pairs run repeats the same few
+        // thousand combinations millions of times: keep the formatted text in a direct-mapped table.
+        const uint64_t key = (((uint64_t)st.r.dist << 32) | st.r.len) + 1;
+        Formatted &f = memo_[(size_t)((key * 0x9E3779B97F4A7C15ull) >> 48)];
+        if (f.key != key) {
+            f.key = key;
+            const double v = mode_ == 'c' ? st.jc_minus_p() : mode_ == 'j' ? st.jc_distance()
+                           : mode_ == 'p' ? st.proportion_different() : st.similarity();
+            f.n = (uint8_t)Out::format(v, f.txt);
+        }
+        if (!matrix_) { names(out, accno1, accno2); out.raw(f.txt, f.n); out.put('\n'); }
+        else { out.raw(f.txt, f.n); out.put(' '); }
+    }
+private:
+    template <class Sink>
+    void names(Sink &out, const std::string &accno1, const std::string &accno2) const {
+        if (names_) { out.put(accno1); out.put(" - "); out.put(accno2); out.put(" | "); }
+    }
+    struct Formatted { uint64_t key = 0; uint8_t n = 0; char txt[23]; };
+    std::vector<Formatted> memo_ = std::vector<Formatted>(1u << 16);
+    const char mode_;
+    const bool matrix_, names_;
 };
 
 // ---- what one replayed pair needs ------------------------------------------------
@@ -182,7 +238,7 @@ struct PairView {
 class Replayer {
 public:
     Replayer(const Options &o, float cut_off, SeqpairBatch &batch, Out &out)
-        : opt_(o), cut_off_(cut_off), batch_(batch), out_(out) {}
+        : opt_(o), cut_off_(cut_off), batch_(batch), out_(out), text_(o.output_mode, o.matrix, o.output_names) {}
 
     std::function<std::string(const PairView &, int)> taxon_of;   // get_taxon_string of side 1 / 2 (src/seqdatabase.h:106-114)
     bool taxon_per_sequence = false;   // taxon_of depends on the sequence only: strings and their ids are kept per sequence
@@ -193,10 +249,8 @@ public:
     MadGroups deviations;
 
     void begin_row(const std::string &accno1) {      // src/pairalign.cpp:594-602
+        text_.begin_row(out_, accno1, n_seq_);
         ++n_seq_;
-        if (n_seq_ > 1) out_.put('\n');
-        if (opt_.output_names) { out_.put(accno1); out_.put(' '); }
-        for (unsigned int i = 1; i < n_seq_; ++i) out_.put(' ');
     }
 
     void pair(const PairView &v, const PairStats &st, const pa_params &params) {
@@ -215,46 +269,12 @@ public:
             out_.put(x); out_.put('\n');
             if (opt_.output_names) { out_.put('>'); out_.put(*v.accno2); out_.put('\n'); }
             out_.put(y); out_.put('\n');
-        } else if (mode == 'd') {
-            if (!opt_.matrix) {
-                names(v);
-                out_.put("Proportion sites that are different (and similarity): ");
-                out_.num(st.proportion_different()); out_.put(" ("); out_.num(st.similarity());
-                out_.put("), Jukes-Cantor distance: "); out_.num(st.jc_distance());
-                out_.put(", difference between the two: "); out_.num(st.jc_minus_p()); out_.put(".\n");
-            } else {
-                out_.num(st.proportion_different()); out_.put('/'); out_.num(st.similarity()); out_.put('/');
-                out_.num(st.jc_distance()); out_.put('/'); out_.num(st.jc_minus_p()); out_.put('.');
-            }
-        } else if (mode == 'c') scalar_memo(v, st, [](const PairStats &q) { return q.jc_minus_p(); });
-        else if (mode == 'j') scalar_memo(v, st, [](const PairStats &q) { return q.jc_distance(); });
-        else if (mode == 'p') scalar_memo(v, st, [](const PairStats &q) { return q.proportion_different(); });
-        else if (mode == 's') scalar_memo(v, st, [](const PairStats &q) { return q.similarity(); });
+        } else if (TextEmitter::handles(mode)) text_.pair(out_, *v.accno1, *v.accno2, st);
         // mode 'C' (-g cluster) falls through every branch of the reference's align_pair: nothing happens
         if (!opt_.quiet) std::cerr << '.';
     }
 
 private:
-    void names(const PairView &v) {
-        if (opt_.output_names) { out_.put(*v.accno1); out_.put(" - "); out_.put(*v.accno2); out_.put(" | "); }
-    }
-    void scalar(const PairView &v, double value) {
-        if (!opt_.matrix) { names(v); out_.num(value); out_.put('\n'); }
-        else { out_.num(value); out_.put(' '); }
-    }
-    // The printed figure depends on (mismatches, columns) only, and an all-pairs run repeats the same few
-    // thousand combinations millions of times: keep the formatted text in a direct-mapped table.
-    struct Formatted { uint64_t key = 0; uint8_t n = 0; char txt[23]; };
-    std::vector<Formatted> memo_ = std::vector<Formatted>(1u << 16);
-    template <class F>
-    void scalar_memo(const PairView &v, const PairStats &st, F value_of) {
-        const uint64_t key = (((uint64_t)st.r.dist << 32) | st.r.len) + 1;
-        Formatted &f = memo_[(size_t)((key * 0x9E3779B97F4A7C15ull) >> 48)];
-        if (f.key != key) { f.key = key; f.n = (uint8_t)Out::format(value_of(st), f.txt); }
-        if (!opt_.matrix) { names(v); out_.raw(f.txt, f.n); out_.put('\n'); }
-        else { out_.raw(f.txt, f.n); out_.put(' '); }
-    }
-
     // src/pairalign.cpp:690-805
     void group(const PairView &v, const PairStats &st) {
         const long a1 = v.cid1, a2 = v.cid2;
@@ -331,6 +351,7 @@ private:
     const float cut_off_;
     SeqpairBatch &batch_;
     Out &out_;
+    TextEmitter text_;
     unsigned int n_seq_ = 0;
     std::vector<std::string> tax_cache_;   // taxon string per sequence (taxon_per_sequence)
     std::vector<int> tax_id_;              // its MadGroups::intern() id, -2: not fetched yet
