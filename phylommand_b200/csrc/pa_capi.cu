@@ -998,7 +998,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             d.launches += 1;
         }
         CU(cudaEventRecord(d.ev[1], d.stream));
-        pa_walk_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
+        pa_walk_kernel<<<(unsigned)((nb + WALK_WARPS - 1) / WALK_WARPS), WALK_WARPS * 32, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
                                                                         d.d_ops_off, d.d_nops, fast ? KFAST : KGEN, KGEN);
         CU(cudaGetLastError());
         d.launches += 1;

@@ -486,20 +486,25 @@ pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, co
 // moves of this pair (16 for A/C/G/T pairs, 8 for the general kernel).
 //
 // The walk is a chain of dependent loads, one row of the move store (a different cache line) per step, and the
-// store of a long pair (226 MB for 30 kb x 30 kb) is in DRAM by the time the walk starts.  Lane 0 walks; every
-// WALK_EPOCH rows all lanes prefetch the lines the path will most likely touch WALK_EPOCH..2*WALK_EPOCH rows
-// further up (the diagonal through the current cell, one line either side of it) into L2, so most steps of the
-// chain wait for L2 instead of DRAM.  The prefetch is a hint: a path that leaves the diagonal is still walked
-// exactly, only slower.
+// store of a long pair (226 MB for 30 kb x 30 kb) is in DRAM by the time the walk starts.  So the warp works in
+// epochs of WALK_EPOCH rows: all lanes fetch, for every row of the NEXT epoch, the 128 slots around the diagonal
+// through the current cell (two 16-byte loads per row, in flight while lane 0 walks the current epoch out of
+// shared memory) and park them in the other half of a double buffer.  A step whose slot lies outside its row's
+// window (the path drifted more than ~32 columns off the diagonal within two epochs) reads global memory instead:
+// the windows are a cache, the walk is exact either way.
 constexpr int WALK_EPOCH = 64;
+constexpr int WALK_WARPS = 4;
+constexpr int WALK_WIN = 128;        // slots per row window (32 bytes)
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-__global__ void pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
-                               const pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
-                               uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
-                               const int k_pure, const int k_general) {
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
+               const pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
+               uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
+               const int k_pure, const int k_general) {
+    __shared__ __align__(16) uint4 win[WALK_WARPS][2][WALK_EPOCH][2];
+    __shared__ int wbase[WALK_WARPS][2][WALK_EPOCH];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= count) return;
     const uint32_t a = ia[e], b = ib[e];
@@ -517,45 +522,67 @@ __global__ void pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint3
     const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : k_general);
     const int P = (m + W - 1) / W;
     const int padL = P * W - m;
-    const size_t stride = (size_t)P * W / 4;
+    const int slots = P * W;                 // >= 256
+    const size_t stride = (size_t)slots / 4;
     const uint8_t *d = dirs + dirs_off[e];
     int i = res[e].end_i, j = res[e].end_j;
-    auto prefetch_rows = [&](int i_top) {      // rows i_top, i_top-1, ...: two per lane, along the diagonal through (i, j)
+    // windows of rows i_top, i_top-1, ... (two per lane) along the diagonal that passes (i_top, slot_top)
+    uint4 w0[2], w1[2];
+    int wb[2];
+    auto fetch = [&](const int i_top, const int slot_top) {
 #pragma unroll
         for (int h = 0; h < WALK_EPOCH / 32; ++h) {
-            const int r = i_top - lane - 32 * h;
-            const int slot = j - (i - r) + padL;
-            if (r >= 0 && slot >= -128) {
-                const int lo = max(slot - 128, 0), hi = min(max(slot + 128, 0), P * W - 1);
-                const uint8_t *row = d + (size_t)r * stride;
-                prefetch_l2(row + (lo >> 2));
-                if ((hi >> 9) != (lo >> 9)) prefetch_l2(row + (hi >> 2));
-            }
+            const int q = lane + 32 * h;
+            const int r = i_top - q;
+            int base = (slot_top - q - WALK_WIN / 2) & ~63;
+            base = min(max(base, 0), slots - WALK_WIN);
+            wb[h] = base;
+            if (r >= 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(d + (size_t)r * stride + (base >> 2));
+                w0[h] = __ldcg(src); w1[h] = __ldcg(src + 1);
+            } else { w0[h] = make_uint4(0, 0, 0, 0); w1[h] = w0[h]; }
         }
     };
-    prefetch_rows(i);
+    auto park = [&](const int buf) {
+#pragma unroll
+        for (int h = 0; h < WALK_EPOCH / 32; ++h) {
+            const int q = lane + 32 * h;
+            win[wib][buf][q][0] = w0[h]; win[wib][buf][q][1] = w1[h];
+            wbase[wib][buf][q] = wb[h];
+        }
+    };
+    fetch(i, j + padL);
+    park(0);
+    __syncwarp();
     if (lane == 0) {
         if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
         else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
     }
-    for (;;) {
+    for (int buf = 0;; buf ^= 1) {
         i = __shfl_sync(FULL_MASK, i, 0);
         j = __shfl_sync(FULL_MASK, j, 0);
         if (i < 0 && j < 0) break;
-        prefetch_rows(i - WALK_EPOCH);
+        const int i_top = i;
+        fetch(i_top - WALK_EPOCH, j + padL - WALK_EPOCH);        // the next epoch's rows, in flight during this walk
         if (lane == 0) {
-            const int i_stop = i - WALK_EPOCH;         // walk until WALK_EPOCH rows are behind us (or the end)
+            const int i_stop = i_top - WALK_EPOCH;                // walk until WALK_EPOCH rows are behind us (or the end)
+            const uint8_t *wbytes = reinterpret_cast<const uint8_t *>(&win[wib][buf][0][0]);
             while ((i >= 0 || j >= 0) && i > i_stop) {
                 uint32_t mv = 3;
                 if (i >= 0 && j >= 0) {
-                    const int slot = j + padL;
-                    mv = (__ldcg(&d[(size_t)i * stride + (slot >> 2)]) >> ((slot & 3) * 2)) & 3u;
+                    const int slot = j + padL, q = i_top - i;
+                    const int rel = slot - wbase[wib][buf][q];
+                    const uint32_t byte = ((unsigned)rel < (unsigned)WALK_WIN) ? wbytes[q * 32 + (rel >> 2)]
+                                                                              : __ldcg(&d[(size_t)i * stride + (slot >> 2)]);
+                    mv = (byte >> ((slot & 3) * 2)) & 3u;
                 }
                 if (mv == 0) { o[k++] = 0; --i; --j; }
                 else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
                 else { o[k++] = 2; --j; }
             }
         }
+        __syncwarp();
+        park(buf ^ 1);
         __syncwarp();
     }
     if (lane == 0) n_ops[e] = k;
