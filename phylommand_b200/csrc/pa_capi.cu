@@ -227,15 +227,18 @@ int ensure_deferred(Device &d, size_t n) {
     return PA_OK;
 }
 
-// Longest sequence the s16x2 kernel may take: every score must stay inside int16.
-uint32_t max_len16(const pa_params &p) {
+// Longest sequence the s16x2 kernel may take with plain 16-bit scores, and the bias B it stores them with
+// (stored = true + B, see duo_row in pa_dp.cuh): true values lie in [-(|ge| L + |mismatch| + |go|), match L], and
+// the stored ones must stay negative (<= -16) and, after one more gap extension, above -32768.  256 of margin.
+uint32_t max_len16(const pa_params &p, int *bias = nullptr) {
     const long long m = p.match > 0 ? p.match : 1;
     const long long ge = p.gap_ext < 0 ? -(long long)p.gap_ext : 1;
     const long long fixed = std::llabs((long long)p.mismatch) + std::llabs((long long)p.gap_open);
-    long long a = 32000 / m, b = (32000 - fixed) / ge;
-    long long r = std::min(a, b);
+    long long r = (32752 - 256 - fixed - ge) / (m + ge);
     if (r < 0) r = 0;
-    return (uint32_t)std::min<long long>(r, 8192);
+    r = std::min<long long>(r, 8192);
+    if (bias) *bias = (int)(-16 - m * r);
+    return (uint32_t)r;
 }
 
 // Launch the kernels for `count` elements (triangle range starting at `first`,
@@ -303,7 +306,9 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         return PA_OK;
     }
     const bool fast = fast_params_ok(p);
-    const uint32_t l16 = fast ? max_len16(p) : 0;
+    int bias16 = 0;
+    const uint32_t l16 = fast ? max_len16(p, &bias16) : 0;
+    sc.bias16 = bias16;
     const bool duo = fast && !d_ia && l16 >= 16 && !c.force_32bit;
     // a CTA per pair pays off when there are too few long pairs to keep every warp of a one-item-per-warp kernel
     // busy; with thousands of them those kernels are the faster ones (no hand-over, no block-count rounding)
@@ -324,7 +329,11 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     const unsigned int *count2 = nullptr;
     if (duo) {
         const uint64_t item_lo = item_of(c, first), item_hi = item_of(c, first + count - 1) + 1;
-        if (c.kduo == 0)
+        if (c.kduo == 0 && p.gap_ext == -1)      // pairalign's own gap extension: the build with GE as an immediate
+            pa_warp_duo_kernel<0, 1, -1><<<d.grid_duo_auto, threads, 0, d.stream>>>(
+                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, amb ? 1 : 0);
+        else if (c.kduo == 0)
             pa_warp_duo_kernel<0><<<d.grid_duo_auto, threads, 0, d.stream>>>(
                 S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, amb ? 1 : 0);
@@ -343,9 +352,14 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         CU(cudaGetLastError());
         d.launches += 1;
         if (amb) {   // the items with sparse ambiguity codes: same work items, AMB variant (its own work counter)
-            pa_warp_duo_kernel<-1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
-                d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
+            if (p.gap_ext == -1)
+                pa_warp_duo_kernel<-1, 1, -1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
+                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
+                    d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
+            else
+                pa_warp_duo_kernel<-1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
+                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
+                    d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
             CU(cudaGetLastError());
             d.launches += 1;
         }
@@ -538,10 +552,14 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_duo3 = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
         d.grid_duo8 = std::max(1, occ) * d.n_sm;
+        // the two builds of a kernel (gap extension at run time / as an immediate) share one grid size: the smaller
+        int occ_c = 0;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo_auto = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo_auto = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<-1>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo_amb = std::max(1, occ) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<-1, 1, -1>, WARPS_PER_CTA * 32, 0);
+        d.grid_duo_amb = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);

@@ -55,7 +55,7 @@ struct SeqStore {
     uint32_t n_seq;
 };
 
-struct Scoring { int match, mismatch, go, ge; };
+struct Scoring { int match, mismatch, go, ge; int bias16 = 0; };   // bias16: see duo_row (s16x2 kernels only)
 
 struct PairSource {
     uint64_t first;          // triangle mode: global index of element 0
@@ -313,6 +313,14 @@ __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
+// BIAS.  Every packed state is stored as true value + B with B < 0 chosen so that both halves are always
+// NEGATIVE (B = sc.bias16 from the host for plain 16-bit scores, WIN_BIAS inside the floating window).  The
+// recurrence only adds constants and takes maxima, so a common bias passes straight through it.  What it buys:
+// H + GO, one of the five packed additions per cell, becomes a plain 32-bit add -- with the low half negative,
+// low + (GO & 0xffff) carries into the high half on every single cell (for GO < 0), so adding the constant
+// GOc = (GO - 1) << 16 | (GO & 0xffff) is exact for both halves.  ptxas issues that add as IMAD.IADD on the FMA
+// pipe; the ALU pipe, which bounds this kernel, has 24 instructions fewer per step of 24 cells (K = 12).
+//
 // One row of the packed recurrence over this lane's K columns.  Reads the
 // previous row from (Hs, C1s, C2s), writes this row to (Hd, C1d, C2d); Gy is
 // updated in place.  Source and destination arrays are different registers
@@ -338,15 +346,18 @@ __device__ __forceinline__ uint32_t vibmax_s16x2(const uint32_t a, const uint32_
     return val;
 }
 
-template <int K>
+// GEC != 0: the gap-extension penalty is the compile-time constant GEC and travels as an immediate operand of
+// VIADDMNMX.S16x2 -- two register reads fewer per cell (measured: +2 % on config 2).
+template <int K, int GEC = 0>
 __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
                                         const uint32_t (&C1s)[K], uint32_t (&C1d)[K],
                                         const uint32_t (&C2s)[K], uint32_t (&C2d)[K],
                                         const uint32_t (&selS)[K], const uint32_t (&selI1)[K], const uint32_t (&selI2)[K],
                                         const uint32_t Rlo, const uint32_t Rhi, const uint32_t Mlo, const uint32_t Mhi,
-                                        const uint32_t GOpk, const uint32_t GEpk,
+                                        const uint32_t GOc, const uint32_t GEpk,
                                         uint32_t hdiag, uint32_t Gl, uint32_t cd1, uint32_t cd2, uint32_t cl1, uint32_t cl2,
                                         uint32_t &Hout, uint32_t &Gxout, uint32_t &c1out, uint32_t &c2out) {
+    const uint32_t GE2 = GEC ? ((uint32_t)GEC & 0xffffu) * 0x10001u : GEpk;
     uint32_t Hdg = hdiag;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -356,9 +367,9 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
         const uint32_t Gu = Gy[k];
         const uint32_t cu1 = C1s[k], cu2 = C2s[k];
         const uint32_t h = __vadd2(__vimax3_s16x2(Hdg, Gu, Gl), s);
-        const uint32_t o = __vadd2(Hdg, GOpk);
-        const uint32_t gy = __viaddmax_s16x2(Gu, GEpk, o);
-        const uint32_t gx = __viaddmax_s16x2(Gl, GEpk, o);
+        const uint32_t o = Hdg + GOc;                                // IMAD.IADD: both halves + GO (see above)
+        const uint32_t gy = __viaddmax_s16x2(Gu, GE2, o);
+        const uint32_t gx = __viaddmax_s16x2(Gl, GE2, o);
         bool pUhi, pUlo, pDhi, pDlo;
         const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);         // gy >= gx
         (void)vibmax_s16x2(h, g, pDhi, pDlo);                        // h >= max(gy, gx)
@@ -383,6 +394,7 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
 // +-WIN_T.  The recurrence itself is untouched: it only ever combines values of one frame.  The edge rows handed to
 // the next pass carry their offsets in a second int4 (bbuf rows 2i, 2i+1), maxima are compared as true 32-bit values.
 constexpr int WIN_T = 8192, WIN_Q = 4096;
+constexpr int WIN_BIAS = -16384;     // centre of the window in stored terms: values stay in about [-29000, -3800]
 
 // AMB (sparse IUPAC ambiguity codes, no gaps): the 2-bit sequences hold a placeholder base at ambiguous positions and
 // the ranges of such positions travel beside them (ex, ey1, ey2: pos | run << 16 | set << 24, in shared memory).
@@ -415,7 +427,7 @@ __device__ __forceinline__ int4 amb_row_table(const int4 *tab, const Scoring sc,
     return make_int4(T.x, (int)Rhi, T.z, (int)Mhi);
 }
 
-template <int K, bool WIN = false, bool AMB = false>
+template <int K, bool WIN = false, bool AMB = false, int GEC = 0>
 __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
                                                const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
                                                const uint32_t vrow, int4 *tab,
@@ -427,9 +439,11 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
     const int mmax = m1 > m2 ? m1 : m2;
     const int P = (mmax + W - 1) / W;
     const int pad1 = P * W - m1, pad2 = P * W - m2;
-    const int Hinit = -sc.go;
+    const int B = WIN ? WIN_BIAS : sc.bias16;      // stored = true + B, negative in both halves (duo_row)
+    const uint32_t Bpk = pack16(B, B);
+    const int Hinit = -sc.go + B;
     const uint32_t HinitPk = pack16(Hinit, Hinit);
-    const uint32_t GOpk = pack16(sc.go, sc.go), GEpk = pack16(sc.ge, sc.ge);
+    const uint32_t GOc = sc.go ? pack16(sc.go, sc.go - 1) : 0u, GEpk = pack16(sc.ge, sc.ge);
 
     int rowBest1 = INT_MIN, rowJ1 = 0, rowBest2 = INT_MIN, rowJ2 = 0;
     uint32_t rowC1 = 0, rowC2 = 0;
@@ -467,8 +481,8 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             tab[z * 4 + xi] = e;
         }
         if (lane == 0) {
-            __stcg(&bbuf[vrow], make_int4((int)HinitPk, 0, 0, 0));
-            if (WIN) __stcg(&bbuf[vrow + 1], make_int4(0, 0, 0, 0));
+            __stcg(&bbuf[vrow], make_int4((int)HinitPk, (int)Bpk, 0, 0));
+            if (WIN) __stcg(&bbuf[vrow + 1], make_int4(-B, -B, 0, 0));
         }
         __syncwarp();
     }
@@ -485,7 +499,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
-            HX[k] = HinitPk; HY[k] = HinitPk; Gy[k] = 0; C1X[k] = 0; C2X[k] = 0; C1Y[k] = 0; C2Y[k] = 0;
+            HX[k] = HinitPk; HY[k] = HinitPk; Gy[k] = Bpk; C1X[k] = 0; C2X[k] = 0; C1Y[k] = 0; C2Y[k] = 0;
             uint32_t c1, c2, i1, i2;
             if (j1 < 0)       { c1 = 5; i1 = 0x5555u; }
             else if (j1 == 0) { c1 = 4; i1 = 0x5654u; }
@@ -510,14 +524,14 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
         }
         // what the left neighbour handed over for the previous odd row: diagonal of the next even row
         uint32_t hprev = HinitPk, c1prev = 0, c2prev = 0;
-        uint32_t HoA = HinitPk, GoA = 0, c1oA = 0, c2oA = 0, HoB = HinitPk, GoB = 0, c1oB = 0, c2oB = 0;
+        uint32_t HoA = HinitPk, GoA = Bpk, c1oA = 0, c2oA = 0, HoB = HinitPk, GoB = Bpk, c1oB = 0, c2oB = 0;
         // lane 0's left edge: rows of the previous pass's right edge, or the virtual row in pass 0
         const int4 *feed = p > 0 ? bbuf : bbuf + vrow;
         const int fmul = p > 0 ? (WIN ? 2 : 1) : 0;
         int4 fA = __ldcg(&feed[0]), fB = __ldcg(&feed[fmul * (n > 1 ? 1 : 0)]);
         int4 fOA = make_int4(0, 0, 0, 0), fOB = fOA;       // WIN: the offsets of the two feed rows
         if (WIN) { fOA = __ldcg(&feed[1]); fOB = __ldcg(&feed[fmul * (n > 1 ? 1 : 0) + 1]); }
-        int off1 = 0, off2 = 0;
+        int off1 = -B, off2 = -B;                 // true value = stored + off
         uint32_t xw = xs[min(max(-2 * lane, 0) >> 4, x_last_word)];
 
         for (int t = 0; t < n_steps; ++t) {
@@ -563,8 +577,8 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     int4 T;
                     if (AMB) T = amb_row_table(tab, sc, mA, iA == 0, a1, a2, spgo1, spgo2);
                     else T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
-                    duo_row<K>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
-                               (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
+                    duo_row<K, GEC>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
+                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
                                hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
                     if (store) {
                         if (WIN) {
@@ -589,8 +603,8 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     int4 T;
                     if (AMB) T = amb_row_table(tab, sc, mB, false, a1, a2, spgo1, spgo2);
                     else T = tab[xi2 >> 2];
-                    duo_row<K>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
-                               (uint32_t)T.z, (uint32_t)T.w, GOpk, GEpk,
+                    duo_row<K, GEC>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
+                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
                                hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
                     if (store) {
                         if (WIN) {
@@ -614,7 +628,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                 hprev = hinB; c1prev = c1inB; c2prev = c2inB;
                 if (WIN) {   // keep this lane's window centred on its right edge
                     const uint32_t edge = (iA + 1 < n) ? HoB : HoA;
-                    const int v1 = lo16(edge), v2 = hi16(edge);
+                    const int v1 = lo16(edge) - B, v2 = hi16(edge) - B;
                     const int d1 = v1 > WIN_T ? WIN_Q : (v1 < -WIN_T ? -WIN_Q : 0);
                     const int d2 = v2 > WIN_T ? WIN_Q : (v2 < -WIN_T ? -WIN_Q : 0);
                     if (d1 | d2) {
@@ -640,7 +654,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
             const uint32_t hk = in_y ? HY[k] : HX[k];
             const uint32_t ck1 = in_y ? C1Y[k] : C1X[k], ck2 = in_y ? C2Y[k] : C2X[k];
-            const int h1 = lo16(hk) + (WIN ? off1 : 0), h2 = hi16(hk) + (WIN ? off2 : 0);
+            const int h1 = lo16(hk) + (WIN ? off1 : -B), h2 = hi16(hk) + (WIN ? off2 : -B);
             if (j1 >= 0 && h1 > bv1) { bv1 = h1; bj1 = j1; bc1 = ck1; }
             if (j2 >= 0 && h2 > bv2) { bv2 = h2; bj2 = j2; bc2 = ck2; }
         }
@@ -662,7 +676,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
     colI2 = __shfl_sync(FULL_MASK, colI2, 31); colC2 = __shfl_sync(FULL_MASK, colC2, 31);
     if (lane == 0) {
         // scores stay far above -32768 (host-checked range), so the sentinel is never a real value
-        const int colBest1 = WIN ? colB1 : lo16(colBestPk), colBest2 = WIN ? colB2 : hi16(colBestPk);
+        const int colBest1 = WIN ? colB1 : lo16(colBestPk) - B, colBest2 = WIN ? colB2 : hi16(colBestPk) - B;
         pa_pair_result o;
         if (res1) {
             if (rowBest1 > colBest1) { o.score = rowBest1; o.end_i = n - 1; o.end_j = rowJ1; o.dist = rowC1 & 0xffffu; o.len = rowC1 >> 16; }
@@ -767,7 +781,8 @@ __host__ __device__ __forceinline__ int duo_pick_k(const int m, const uint32_t k
 }
 
 // K = 0: the strip width is chosen per work item (duo_pick_k); K > 0: fixed.
-template <int K, int MINB = 1>
+// GEC: compile-time gap extension (the host launches the GEC = -1 build for pairalign's own scoring), 0 = sc.ge.
+template <int K, int MINB = 1, int GEC = 0>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
                    const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
@@ -852,27 +867,27 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
             }
             __syncwarp();
             if (too_long)
-                align_warp_duo<12, true, true>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane,
+                align_warp_duo<12, true, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane,
                                                excs[wib][0], nx, excs[wib][1], ny1, excs[wib][2], ny2);
             else
-                align_warp_duo<12, false, true>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane,
+                align_warp_duo<12, false, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane,
                                                 excs[wib][0], nx, excs[wib][1], ny1, excs[wib][2], ny2);
         } else if constexpr (K == 0) {
             if (too_long) {
                 // bbuf rows come in pairs here (values, offsets); the virtual-column row is the last pair
-                align_warp_duo<12, true>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane);
+                align_warp_duo<12, true, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane);
                 continue;
             }
             // strip width per work item: the fewest issue slots for these lengths (duo_pick_k)
             switch (duo_pick_k(my1 > my2 ? my1 : my2, kmask & DUO_KSET, step_cost)) {
-                case 8:  align_warp_duo<8>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 10: align_warp_duo<10>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 11: align_warp_duo<11>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 12: align_warp_duo<12>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                default: align_warp_duo<DUO_KMAX>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 8:  align_warp_duo<8, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 10: align_warp_duo<10, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 11: align_warp_duo<11, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 12: align_warp_duo<12, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                default: align_warp_duo<DUO_KMAX, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
             }
         } else {
-            align_warp_duo<K>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane);
+            align_warp_duo<K, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane);
         }
     }
 }

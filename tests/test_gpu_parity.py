@@ -309,19 +309,27 @@ def test_long_pair_many_passes(gpu, oracle):
 
 
 def test_s16x2_kernel_near_its_int16_limit(gpu, oracle):
-    """4.5 kb sequences: scores reach 31,500 (identical pair) and stay inside int16; a longer one switches its work
-    items to the floating-window variant of the same kernel."""
-    _, seqs = synth.make_long(3, 77, length=4450, spread=0.02, div_lo=0.0, div_hi=0.05)
+    """4 kb sequences: scores reach 28 000 (identical pair); stored with the kernel's negative bias they come within
+    a few dozen of 0 from below, the other end of the range stays inside int16 (max_len16 = 4059 for pairalign's
+    scoring).  A longer sequence switches its work items to the floating-window variant of the same kernel."""
+    _, seqs = synth.make_long(3, 77, length=3970, spread=0.02, div_lo=0.0, div_hi=0.05)
     enc = [synth.to_masks(s) for s in seqs]
     enc.append(enc[0].copy())                       # identical to sequence 0: the highest possible score
+    rng = np.random.default_rng(79)
+    enc.append(synth.to_masks(synth.BASES[rng.integers(0, 4, size=4059)]))   # exactly the limit, unrelated to the others
+    enc.append(np.full(4059, 1, dtype=np.uint8))    # poly-A at the limit: identical pair below scores 7 * 4059
+    enc.append(np.full(4059, 1, dtype=np.uint8))
+    enc.append(np.full(4058, 8, dtype=np.uint8))    # poly-T: every column a mismatch against poly-A
     _, longer = synth.make_long(1, 78, length=4700, spread=0.0)
-    enc.append(synth.to_masks(longer[0]))           # above max_len16 = 4571: floating-window variant
+    enc.append(synth.to_masks(longer[0]))           # above max_len16: floating-window variant
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     t = gpu.timing()
     assert t["dp_duo_ms"] > 0 and t["dp_fast_ms"] == 0.0 and t["dp_cta_ms"] == 0.0
-    _same(got, _oracle_all(oracle, enc))
+    _same(got, _oracle_all(oracle, enc, threads=12))
     assert int(got[2]["score"]) == 7 * len(enc[0])  # pair (0, 3)
+    scores = {(a, b): int(got[k]["score"]) for k, (a, b) in enumerate((a, b) for a in range(len(enc)) for b in range(a + 1, len(enc)))}
+    assert scores[(5, 6)] == 7 * 4059
 
 
 def test_floating_window_s16x2_long_pairs(gpu, oracle):
