@@ -362,8 +362,8 @@ def main() -> None:
             achieved = OPS_PER_CELL * my_cells / (kern_step_ms * 1e-3) / 1e9
             line["roofline"] = {
                 "bound": "int32", "achieved": achieved, "peak": peak_ops, "unit": "Gop/s", "frac": achieved / peak_ops,
-                "traffic": 7169024 if (args.workload == "c2" and world == 1) else None,
-                "kernel": "pa_warp_duo_kernel<0> (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per lane chosen per work item)",
+                "traffic": 7372288 if (args.workload == "c2" and world == 1) else None,
+                "kernel": "pa_warp_duo_kernel<0,1,-1> (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per lane chosen per work item, biased storage with H+GO on the FMA pipe)",
                 "kernel_ms_per_step": kern_step_ms, "kernel_gcups": my_cells / (kern_step_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL,
                 "achieved_def": "14 integer operations per DP cell (SURVEY.md 8d) x cells of this rank / CUDA-event time of the DP kernels",
@@ -371,7 +371,7 @@ def main() -> None:
                             "all SMs, measured in this run by pa_int32_peak",
                 "frac_vs_32bit_lane_roofline": achieved / alu32, "peak_32bit_lane": alu32,
                 "traffic_def": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                               "(profiles/r01_v4_duo_auto_ncu_full.txt: 1.40 MB read + 5.77 MB written); algorithmic bytes per launch are in hbm.algorithmic_bytes_per_step",
+                               "(profiles/r01_v5_duo_bias_ncu_full.txt: 0.99 MB read + 6.39 MB written); algorithmic bytes per launch are in hbm.algorithmic_bytes_per_step",
                 "measured": {k: {"gops": v[0], "sm_mhz": v[1]} for k, v in peak.items()},
                 "hbm": {"algorithmic_bytes_per_step": int(masks.nbytes // 4 + count * 20),
                         "note": "2-bit sequences + 20 B per pair; HBM is not the bound (SURVEY.md 8d)"},

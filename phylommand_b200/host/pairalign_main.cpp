@@ -549,7 +549,17 @@ void run_fasta(const Options &opt, Out &out) {
                     batch.alignments(params, ia_b, ib_b, opb[(first / chunk_pairs) & 1]);
                 }
             };
-            pipeline(total, chunk_pairs, produce, consume);
+            double replay_ms = 0, produce_ms = 0;       // busy time of the two sides of the pipeline (PAIRALIGN_TIMING)
+            auto timed = [&](double &acc, auto &&fn) {
+                const auto t0 = std::chrono::steady_clock::now();
+                fn();
+                acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            };
+            pipeline(total, chunk_pairs,
+                     [&](uint64_t first, uint64_t n, pa_pair_result *dst) { timed(produce_ms, [&] { produce(first, n, dst); }); },
+                     [&](uint64_t first, const std::vector<pa_pair_result> &recs) { timed(replay_ms, [&] { consume(first, recs); }); });
+            if (timer.on)
+                std::cerr << "[pairalign_b200] pipeline busy: align " << produce_ms << " ms, replay + print " << replay_ms << " ms" << std::endl;
             if (timer.on) {
                 pa_timing tm;
                 if (pa_get_timing(&tm) == PA_OK)
