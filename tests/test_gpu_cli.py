@@ -89,4 +89,3 @@ def test_cli_two_devices_same_output(exe, workdir):
     env = dict(os.environ, PAIRALIGN_DEVICES="0,1")
     r = subprocess.run([str(exe), "-j", "-n", "-m", "pure.fst"], cwd=workdir, capture_output=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout == want
-
