@@ -522,17 +522,27 @@ int pa_init(const int *devices, int n_dev) {
     std::vector<int> ids;
     if (!devices || n_dev <= 0) ids.push_back(0);
     else for (int k = 0; k < n_dev; ++k) ids.push_back(devices[k]);
+    for (int id : ids)
+        if (id < 0 || id >= avail) return fail(PA_EINVAL, "device %d out of range (0..%d)", id, avail - 1);
+    if (ids.size() > 1) {
+        // Primary contexts take most of a second each; create them side by side, one host thread per device
+        // (errors surface again in the sequential set-up below).
+        std::vector<std::thread> th;
+        for (int id : ids) th.emplace_back([id] { if (cudaSetDevice(id) == cudaSuccess) cudaFree(nullptr); });
+        for (auto &t : th) t.join();
+    }
     Context *c = new Context();
     for (int id : ids) {
-        if (id < 0 || id >= avail) { delete c; return fail(PA_EINVAL, "device %d out of range (0..%d)", id, avail - 1); }
         Device d;
         d.id = id;
-        cudaDeviceProp prop;
-        if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess) {
+        int major = 0, minor = 0, n_sm = 0;
+        if (cudaSetDevice(id) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, id) != cudaSuccess ||
+            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, id) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, id) != cudaSuccess) {
             delete c; return fail(PA_ECUDA, "cannot select device %d", id);
         }
-        if (prop.major < 10) { delete c; return fail(PA_ENODEVICE, "device %d is sm_%d%d; this module is built for sm_100a only", id, prop.major, prop.minor); }
-        d.n_sm = prop.multiProcessorCount;
+        if (major < 10) { delete c; return fail(PA_ENODEVICE, "device %d is sm_%d%d; this module is built for sm_100a only", id, major, minor); }
+        d.n_sm = n_sm;
         c->dev.push_back(d);
     }
     for (auto &d : c->dev) {
