@@ -165,7 +165,10 @@ int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b,
  * 0 = a base of x over a base of y, 1 = a base of x over a gap, 2 = a gap over a base of y
  * (bases are consumed from the encoded sequences in order).  op_offsets (count+1 entries) is filled by
  * the call with the prefix sum of len(ia[k]) + len(ib[k]); ops_cap must be at least op_offsets[count].
- * res (optional) receives the pair records.  Pairs are processed in batches sized to device memory. */
+ * res (optional) receives the pair records.  Replaces get_x()/get_y() after align() (src/seqpair.h:83-84,
+ * src/seqpair.cpp:146-188) for every pair of the loop.  Every device of the context takes a contiguous share
+ * of the list (balanced by DP cells); on each, pairs are processed in batches sized to device memory
+ * (2 bits per DP cell). */
 int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
                        uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res);
 
