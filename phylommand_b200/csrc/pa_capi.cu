@@ -319,8 +319,13 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     // (a gap extension beyond -1024 could wrap a 16-bit half before the maximum with the opening term is taken)
     // sequences with sparse IUPAC codes: a second launch of the s16x2 kernel in its AMB form takes their items
     const bool amb = duo && c.kduo == 0 && c.any_sparse && !c.no_amb;
+    // ... and the values a lane holds at one time (13 columns, two rows, what its neighbour hands over) must fit the
+    // window around its right edge with the storage bias in place: about 4000 either side of the re-base band
+    // (stored values stay in [-32768 + |ge|, -16]); neighbouring states differ by at most one of each penalty
+    const long long win_spread = 13ll * (std::llabs((long long)p.match) + std::llabs((long long)p.mismatch) +
+                                         std::llabs((long long)p.gap_open) + std::llabs((long long)p.gap_ext));
     const bool win = duo && c.kduo == 0 && !c.no_win && c.max_len > l16 && !route_long && p.gap_ext >= -1024 &&
-                     (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
+                     win_spread <= 3500 && (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;
     CU(cudaEventRecord(d.ev[0], d.stream));
