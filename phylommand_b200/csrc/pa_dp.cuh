@@ -94,6 +94,10 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
+// compile-time switches handed to generic lambdas
+struct FlagFalse { static constexpr bool value = false; };
+struct FlagTrue { static constexpr bool value = true; };
+
 // ---------------------------------------------------------------------------
 // One pair on one warp.  xs/ys: packed codes (2-bit when !GENERAL, 4-bit sets
 // when GENERAL), generic pointers (shared staging or global).
@@ -141,6 +145,11 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
         uint32_t C[K];
         uint32_t selS[K];   // !GENERAL: PRMT selector of the score byte;   GENERAL: 4-bit set of the column
         uint32_t selI[K];   // !GENERAL: PRMT selector of the count increment; GENERAL: 0 normal, 1 column 0, 2 pad
+        // GENERAL: what a cell of this column scores / counts when the two sets do not intersect -- the mismatch score
+        // and (1 column, 1 mismatch), or INT_MIN and nothing when the column is a gap character.  The row has the same
+        // pair of constants; a cell takes the smaller of the two (src/seqpair.cpp:192-193: either side empty -> INT_MIN).
+        int cXG[GENERAL ? K : 1];
+        uint32_t cInc[GENERAL ? K : 1];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j = j0 + k;
@@ -152,6 +161,8 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
             } else {
                 if (j < 0)       { selS[k] = 0; selI[k] = 2; }
                 else             { selS[k] = fetch4(ys, j); selI[k] = (j == 0) ? 1u : 0u; }
+                cXG[k] = selS[k] ? sc.mismatch : INT_MIN;
+                cInc[k] = selS[k] ? 0x10001u : 0u;
             }
         }
         int hprev = Hinit;
@@ -211,40 +222,42 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                         Gl = gx; cl = c;
                     }
                 } else {
-                    const bool xgap = (xi == 0);
-                    const int sM = xgap ? INT_MIN : sc.match;
-                    const int sX = xgap ? INT_MIN : sc.mismatch;
+                    // xi == 0: a gap character in x -- every cell of the row scores INT_MIN and counts nothing
+                    const int rXG = xi ? sc.mismatch : INT_MIN;
+                    const uint32_t rInc = xi ? 0x10001u : 0u;
                     const bool row0 = (i == 0);
                     uint32_t mv = 0;
+                    // EDGE: this pass holds pad slots and / or column 0 (pass 0 only); the other passes carry no flags
+                    auto cells = [&](auto edge_c) {
+                        constexpr bool EDGE = decltype(edge_c)::value;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const uint32_t ym = selS[k];
-                        const uint32_t fl = selI[k];
-                        const uint32_t both = xi & ym;
-                        int s = both ? sM : sX;
-                        if (ym == 0) s = INT_MIN;
-                        const int Gu = Gy[k];
-                        const uint32_t cu = C[k];
-                        int mx = Hd > Gu ? Hd : Gu;
-                        mx = mx > Gl ? mx : Gl;
-                        int h = wadd(mx, s);
-                        const int o = wadd(Hd, sc.go);
-                        const int uy = wadd(Gu, sc.ge), lx = wadd(Gl, sc.ge);
-                        int gy = o > uy ? o : uy;
-                        int gx = o > lx ? o : lx;
-                        if (row0 || fl != 0) { gy = 0; gx = 0; }
-                        if (fl == 2) h = 0;
-                        const bool pD = (h >= gy) && (h >= gx);
-                        const bool pU = (gy >= gx);
-                        uint32_t inc = 0;
-                        if (!xgap && ym != 0) inc = 0x10000u + (both == 0 ? 1u : 0u);
-                        uint32_t c = pD ? cd + inc : (pU ? cu : cl);
-                        if (fl == 2) c = 0;
-                        if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
-                        Hd = H[k]; cd = cu;
-                        H[k] = h; Gy[k] = gy; C[k] = c;
-                        Gl = gx; cl = c;
-                    }
+                        for (int k = 0; k < K; ++k) {
+                            const uint32_t ym = selS[k];
+                            const bool hit = (xi & ym) != 0;
+                            const int s = hit ? sc.match : min(rXG, cXG[k]);
+                            const uint32_t inc = hit ? 0x10000u : min(rInc, cInc[k]);
+                            const int Gu = Gy[k];
+                            const uint32_t cu = C[k];
+                            int h = wadd(__vimax3_s32(Hd, Gu, Gl), s);
+                            const int o = wadd(Hd, sc.go);
+                            int gy = max(o, wadd(Gu, sc.ge));
+                            int gx = max(o, wadd(Gl, sc.ge));
+                            if (EDGE) {
+                                const uint32_t fl = selI[k];
+                                if (row0 || fl != 0) { gy = 0; gx = 0; }
+                                if (fl == 2) h = 0;
+                            } else if (row0) { gy = 0; gx = 0; }
+                            const bool pD = (h >= gy) && (h >= gx);
+                            const bool pU = (gy >= gx);
+                            uint32_t c = pD ? cd + inc : (pU ? cu : cl);
+                            if (EDGE && selI[k] == 2) c = 0;
+                            if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
+                            Hd = H[k]; cd = cu;
+                            H[k] = h; Gy[k] = gy; C[k] = c;
+                            Gl = gx; cl = c;
+                        }
+                    };
+                    if (p == 0) cells(FlagTrue{}); else cells(FlagFalse{});
                     if (DIRS) {   // 2 bits per slot, row-major, K/4 bytes per lane (K = 8: one 16-bit store)
                         static_assert(!DIRS || K == 8, "the move store assumes K = 8");
                         reinterpret_cast<uint16_t *>(dirs)[(size_t)i * ((size_t)P * 32) + (size_t)p * 32 + lane] = (uint16_t)mv;
