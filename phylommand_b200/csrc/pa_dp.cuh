@@ -244,9 +244,9 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                             int gx = max(o, wadd(Gl, sc.ge));
                             if (EDGE) {
                                 const uint32_t fl = selI[k];
-                                if (row0 || fl != 0) { gy = 0; gx = 0; }
+                                if (fl != 0) { gy = 0; gx = 0; }
                                 if (fl == 2) h = 0;
-                            } else if (row0) { gy = 0; gx = 0; }
+                            }
                             const bool pD = (h >= gy) && (h >= gx);
                             const bool pU = (gy >= gx);
                             uint32_t c = pD ? cd + inc : (pU ? cu : cl);
@@ -257,7 +257,24 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                             Gl = gx; cl = c;
                         }
                     };
-                    if (p == 0) cells(FlagTrue{}); else cells(FlagFalse{});
+                    if (row0) {
+                        // first row: H = s, Gy = Gx = 0 (src/seqpair.cpp:103-107), so the move is D iff s >= 0 and the
+                        // counters start there; no recurrence, and the other rows need no first-row test
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const bool hit = (xi & selS[k]) != 0;
+                            const int s = hit ? sc.match : min(rXG, cXG[k]);
+                            const uint32_t inc = hit ? 0x10000u : min(rInc, cInc[k]);
+                            const int h = (selI[k] == 2) ? 0 : s;
+                            const bool pD = (h >= 0);
+                            const uint32_t c = pD ? inc : 0u;
+                            if (DIRS) mv |= (pD ? 0u : 1u) << (2 * k);
+                            H[k] = h; Gy[k] = 0; C[k] = c;
+                            cl = c;
+                        }
+                        Gl = 0;
+                    } else if (p == 0) cells(FlagTrue{});
+                    else cells(FlagFalse{});
                     if (DIRS) {   // 2 bits per slot, row-major, K/4 bytes per lane (K = 8: one 16-bit store)
                         static_assert(!DIRS || K == 8, "the move store assumes K = 8");
                         reinterpret_cast<uint16_t *>(dirs)[(size_t)i * ((size_t)P * 32) + (size_t)p * 32 + lane] = (uint16_t)mv;
