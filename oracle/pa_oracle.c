@@ -83,9 +83,9 @@ static void stats_over_columns(const uint8_t *ax, const uint8_t *ay, int32_t n,
     *len = l;
 }
 
-int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
-                         int32_t match, int32_t mismatch, int32_t GO, int32_t GE,
-                         pa_oracle_result *res, uint8_t *ax_out, uint8_t *ay_out, int32_t *alen_out) {
+static int align_full_impl(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                           int32_t match, int32_t mismatch, int32_t GO, int32_t GE,
+                           pa_oracle_result *res, uint8_t *ax_out, uint8_t *ay_out, int32_t *alen_out, uint8_t *ops_out) {
     if (n <= 0 || m <= 0 || !res) return -1;
     size_t cells = (size_t)n * (size_t)m;
     int32_t *A = (int32_t *)malloc(cells * sizeof(int32_t));    /* aligned  :98 */
@@ -93,7 +93,8 @@ int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t 
     int32_t *Gx = (int32_t *)malloc(cells * sizeof(int32_t));   /* gap_x    :100 */
     uint8_t *rx = (uint8_t *)malloc((size_t)n + m + 1);
     uint8_t *ry = (uint8_t *)malloc((size_t)n + m + 1);
-    if (!A || !Gy || !Gx || !rx || !ry) { free(A); free(Gy); free(Gx); free(rx); free(ry); return -1; }
+    uint8_t *ro = (uint8_t *)malloc((size_t)n + m + 1);   /* 0: x over y, 1: x over a gap, 2: a gap over y */
+    if (!A || !Gy || !Gx || !rx || !ry || !ro) { free(A); free(Gy); free(Gx); free(rx); free(ry); free(ro); return -1; }
 
 #define AT(M_, i_, j_) M_[(size_t)(i_) * (size_t)m + (size_t)(j_)]
     for (int32_t i = 0; i < n; ++i) {
@@ -130,17 +131,17 @@ int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t 
 
     int32_t k = 0;
     if (i < n - 1) {                                             /* :146-151 */
-        for (int32_t pos = n - 1; pos > i; --pos) { rx[k] = x[pos]; ry[k] = 0; ++k; }
+        for (int32_t pos = n - 1; pos > i; --pos) { rx[k] = x[pos]; ry[k] = 0; ro[k] = 1; ++k; }
     } else if (j < m - 1) {                                      /* :152-157 */
-        for (int32_t pos = m - 1; pos > j; --pos) { rx[k] = 0; ry[k] = y[pos]; ++k; }
+        for (int32_t pos = m - 1; pos > j; --pos) { rx[k] = 0; ry[k] = y[pos]; ro[k] = 2; ++k; }
     }
     while (i >= 0 || j >= 0) {                                   /* :159-178 */
         if (i >= 0 && j >= 0 && AT(A, i, j) >= AT(Gy, i, j) && AT(A, i, j) >= AT(Gx, i, j)) {
-            rx[k] = x[i]; ry[k] = y[j]; ++k; --i; --j;
+            rx[k] = x[i]; ry[k] = y[j]; ro[k] = 0; ++k; --i; --j;
         } else if (j < 0 || (i >= 0 && AT(Gy, i, j) >= AT(A, i, j) && AT(Gy, i, j) >= AT(Gx, i, j))) {
-            rx[k] = x[i]; ry[k] = 0; ++k; --i;
+            rx[k] = x[i]; ry[k] = 0; ro[k] = 1; ++k; --i;
         } else if (i < 0 || (j >= 0 && AT(Gx, i, j) >= AT(A, i, j) && AT(Gx, i, j) >= AT(Gy, i, j))) {
-            rx[k] = 0; ry[k] = y[j]; ++k; --j;
+            rx[k] = 0; ry[k] = y[j]; ro[k] = 2; ++k; --j;
         }
     }
 #undef AT
@@ -148,13 +149,29 @@ int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t 
     for (int32_t a = 0, b = k - 1; a < b; ++a, --b) {
         uint8_t t = rx[a]; rx[a] = rx[b]; rx[b] = t;
         t = ry[a]; ry[a] = ry[b]; ry[b] = t;
+        t = ro[a]; ro[a] = ro[b]; ro[b] = t;
     }
     stats_over_columns(rx, ry, k, &res->dist, &res->len);
     if (ax_out) memcpy(ax_out, rx, (size_t)k);
     if (ay_out) memcpy(ay_out, ry, (size_t)k);
     if (alen_out) *alen_out = k;
-    free(A); free(Gy); free(Gx); free(rx); free(ry);
+    if (ops_out) memcpy(ops_out, ro, (size_t)k);
+    free(A); free(Gy); free(Gx); free(rx); free(ry); free(ro);
     return 0;
+}
+
+int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                         int32_t match, int32_t mismatch, int32_t GO, int32_t GE,
+                         pa_oracle_result *res, uint8_t *ax_out, uint8_t *ay_out, int32_t *alen_out) {
+    return align_full_impl(x, n, y, m, match, mismatch, GO, GE, res, ax_out, ay_out, alen_out, NULL);
+}
+
+/* The same walk as one op byte per aligned column (what pa_align_pairs_ops returns): needed where the gapped
+ * mask strings are ambiguous, i.e. when a sequence itself holds '-' (mask 0). */
+int pa_oracle_align_ops(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                        int32_t match, int32_t mismatch, int32_t GO, int32_t GE,
+                        pa_oracle_result *res, uint8_t *ops_out, int32_t *alen_out) {
+    return align_full_impl(x, n, y, m, match, mismatch, GO, GE, res, NULL, NULL, alen_out, ops_out);
 }
 
 /* Forward-only form.  The traceback's move at (i,j) depends only on the three

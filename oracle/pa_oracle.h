@@ -65,6 +65,12 @@ int pa_oracle_align_full(const uint8_t *x, int32_t n, const uint8_t *y, int32_t 
  * reference's traceback path are carried through the DP (every cell has one
  * predecessor: src/seqpair.cpp:159-178), O(m) memory.  Bit-identical results
  * to pa_oracle_align_full. */
+/* pa_oracle_align_full's walk as op bytes in alignment order: 0 = x[i] over y[j], 1 = x[i] over a gap,
+ * 2 = a gap over y[j] (src/seqpair.cpp:146-188). */
+int pa_oracle_align_ops(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                        int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
+                        pa_oracle_result *res, uint8_t *ops, int32_t *alen);
+
 int pa_oracle_align_forward(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
                             int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
                             pa_oracle_result *res);

@@ -147,8 +147,9 @@ class RefSeqpair:
 
 
 def ensure_built() -> None:
-    if not ORACLE_SO.exists():
-        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "all"], check=True)
+    srcs = [ROOT / "oracle" / n for n in ("pa_oracle.c", "pa_oracle.h", "nj_oracle.c")]
+    if not ORACLE_SO.exists() or any(s.stat().st_mtime > ORACLE_SO.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), str(ORACLE_SO)], check=True)
 
 
 def load() -> Oracle:

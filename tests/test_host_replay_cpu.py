@@ -1,0 +1,70 @@
+"""The command line's host side on a machine WITHOUT a GPU: build/pairalign_hosttest is the product's own
+host code (FASTA index and order, pipeline, matrix framing, number formatting, single-link clusters, MAD
+groups, pair-FASTA input, rendering of alignments) linked with a test double of its device half
+(tests/host_double/seqpair_batch_oracle.cpp: records and op strings from the oracle).  Its output must be
+byte for byte what the reference's pairalign printed (tests/golden/cli/*.out, made by
+oracle/make_cli_golden.py from the unmodified reference).  The product binary build/pairalign_b200 never
+contains the double; tests/test_gpu_cli.py runs the same command lines through the CUDA module."""
+import json
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+CLI_DIR = ROOT / "tests" / "golden" / "cli"
+MANIFEST = json.loads((CLI_DIR / "manifest.json").read_text())
+HOST = ROOT / "phylommand_b200" / "host"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from phylommand_b200 import build
+    from tests import oracle_lib
+    build.build_library()
+    oracle_lib.load()                                            # builds oracle/liboracle.so
+    out = ROOT / "build" / "pairalign_hosttest"
+    out.parent.mkdir(exist_ok=True)
+    srcs = [HOST / "pairalign_main.cpp", HOST / "fasta_index.cpp", HOST / "mad_groups.cpp", HOST / "seqpair_batch.cpp",
+            ROOT / "tests" / "host_double" / "seqpair_batch_oracle.cpp"]
+    assert not any(s.name == "seqpair_batch_device.cpp" for s in srcs)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(out), *map(str, srcs),
+           "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle"),
+           "-L", str(build.LIB_DIR), "-lpairalign_b200", "-Wl,-rpath," + str(build.LIB_DIR), "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return out
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("hostcli")
+    shutil.copytree(CLI_DIR / "inputs", d / "cli" / "inputs")
+    shutil.copytree(ROOT / "tests" / "golden" / "example_files", d / "example_files")
+    return d / "cli" / "inputs"
+
+
+@pytest.mark.parametrize("entry", MANIFEST, ids=[e["tag"] for e in MANIFEST])
+def test_host_side_matches_reference(exe, workdir, entry):
+    cmd = [str(exe), *entry["flags"]] + ([entry["input"]] if entry["input"] else [])
+    r = subprocess.run(cmd, cwd=workdir, capture_output=True, timeout=900)
+    assert r.returncode == entry["rc"], r.stderr.decode(errors="replace")[-2000:]
+    want = (CLI_DIR / f"{entry['tag']}.out").read_bytes()
+    if r.stdout != want:
+        got_lines, want_lines = r.stdout.split(b"\n"), want.split(b"\n")
+        for k, (g, w) in enumerate(zip(got_lines, want_lines)):
+            if g != w:
+                pytest.fail(f"line {k} differs:\n got  {g[:300]!r}\n want {w[:300]!r}\nstderr: {r.stderr.decode(errors='replace')[-500:]}")
+        pytest.fail(f"length differs: got {len(r.stdout)} bytes, want {len(want)}")
+    if entry.get("alignment_groups"):
+        made = (workdir / (entry["input"] + ".alignment_groups")).resolve()
+        assert made.read_bytes() == (CLI_DIR / f"{entry['tag']}.alignment_groups").read_bytes()
+        made.unlink()
+
+
+def test_product_binary_has_no_double():
+    """The double lives under tests/ and the product build never sees it."""
+    from phylommand_b200 import build
+    import inspect
+    assert "host_double" not in inspect.getsource(build)
+    assert (HOST / "seqpair_batch_device.cpp").exists()
