@@ -68,3 +68,39 @@ def test_product_binary_has_no_double():
     import inspect
     assert "host_double" not in inspect.getsource(build)
     assert (HOST / "seqpair_batch_device.cpp").exists()
+
+
+# ---- treeator -n: the host side of build/treeator_b200 (matrix reader, newick printer) ---------------------------------
+NJ_GOLD = ROOT / "tests" / "golden" / "nj"
+NJ_CASES = json.loads((NJ_GOLD / "manifest.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def nj_exe():
+    from phylommand_b200 import build
+    from tests import oracle_lib
+    build.build_library()
+    oracle_lib.load()
+    out = ROOT / "build" / "treeator_hosttest"
+    out.parent.mkdir(exist_ok=True)
+    srcs = [ROOT / "phylommand_b200" / "host_nj" / "treeator_nj_main.cpp", ROOT / "tests" / "host_double" / "nj_build_oracle.cpp"]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(out), *map(str, srcs),
+           "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle"),
+           "-L", str(build.LIB_DIR), "-lpairalign_b200", "-Wl,-rpath," + str(build.LIB_DIR)]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return out
+
+
+@pytest.mark.parametrize("case", NJ_CASES, ids=[c["tag"] for c in NJ_CASES])
+def test_treeator_host_side_matches_reference(nj_exe, case):
+    r = subprocess.run([str(nj_exe), *case["flags"], f"{case['tag']}.matrix"], cwd=NJ_GOLD, capture_output=True, timeout=600)
+    assert r.returncode == case["rc"], r.stderr.decode(errors="replace")[-2000:]
+    assert r.stdout == (NJ_GOLD / f"{case['tag']}.newick").read_bytes()
+
+
+def test_treeator_host_side_stdin_and_ragged(nj_exe):
+    data = (NJ_GOLD / "synth_ties_17.matrix").read_bytes()
+    r = subprocess.run([str(nj_exe), "-n"], input=data, capture_output=True, timeout=600)
+    assert r.returncode == 0 and r.stdout == (NJ_GOLD / "synth_ties_17.newick").read_bytes()
+    r = subprocess.run([str(nj_exe), "-n"], input=b"a 1 2\nb 3 4\nc\n", capture_output=True, timeout=600)
+    assert r.returncode == 1 and b"Error in distance matrix" in r.stderr
