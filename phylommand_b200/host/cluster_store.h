@@ -24,7 +24,12 @@ public:
         has_key_.assign(n, 0);
         members_.assign(n, std::set<long>());
         member_of_.assign(n, std::vector<long>());
+        ghost_.assign(n, 0);
     }
+    // A file with ONE sequence: the reference still visits a pair whose second iterator is end() -- empty accession,
+    // empty sequence, similarity 1 -- and with a cut-off below 1 the only sequence becomes a lead with the empty name
+    // as its member: its cluster line ends in a blank ("only \n"; -O0 and -O2 builds agree).
+    void add_ghost_member(long lead) { ghost_[lead] = 1; }
     // get_cluster (src/seqdatabase.h:203-211): LEAD if it heads a cluster, else the
     // first (lowest) lead whose member set holds it, else EMPTY
     long get_cluster(long accno) const {
@@ -61,6 +66,7 @@ public:
         for (size_t l = 0; l < has_key_.size(); ++l) {
             if (!has_key_[l]) continue;
             out << name_of((long)l);
+            if (ghost_[l]) out << ' ';                      // the empty accession sorts first in the reference's set
             for (long m : members_[l]) out << ' ' << name_of(m);
             out << '\n';
         }
@@ -82,6 +88,7 @@ private:
     std::vector<char> has_key_;
     std::vector<std::set<long>> members_;
     std::vector<std::vector<long>> member_of_;
+    std::vector<char> ghost_;
 };
 
 }  // namespace pab

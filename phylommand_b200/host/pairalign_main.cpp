@@ -279,6 +279,12 @@ private:
     void group(const PairView &v, const PairStats &st) {
         const long a1 = v.cid1, a2 = v.cid2;
         if (taxon_per_sequence && v.seq2 >= 0) { group_cached(v, st); return; }
+        if (v.seq2 < 0 && cut_off_ > 0.000000001 && st.similarity() > cut_off_) {
+            // one sequence in the file: it absorbs the reference's empty second accession (ClusterStore::add_ghost_member)
+            upd(a1, ClusterStore::LEAD, true);
+            clusters.add_ghost_member(a1);
+            return;
+        }
         const std::string tax1 = taxon_of(v, 1), tax2 = v.seq2 >= 0 ? taxon_of(v, 2) : std::string();
         if (cut_off_ > 0.000000001 && v.seq2 >= 0) {
             const long c1 = clusters.get_cluster(a1), c2 = clusters.get_cluster(a2);

@@ -6,6 +6,7 @@ byte for byte what the reference's pairalign printed (tests/golden/cli/*.out, ma
 oracle/make_cli_golden.py from the unmodified reference).  The product binary build/pairalign_b200 never
 contains the double; tests/test_gpu_cli.py runs the same command lines through the CUDA module."""
 import json
+import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -16,6 +17,19 @@ ROOT = Path(__file__).resolve().parent.parent
 CLI_DIR = ROOT / "tests" / "golden" / "cli"
 MANIFEST = json.loads((CLI_DIR / "manifest.json").read_text())
 HOST = ROOT / "phylommand_b200" / "host"
+
+
+def _compile(out, deps, srcs, lib_dir, extra):
+    """g++ into a private name, then an atomic rename: several pytest-xdist workers may build at the same time."""
+    deps = list(deps) + [ROOT / "oracle" / "liboracle.so", ROOT / "include" / "pairalign_b200.h"]
+    if out.exists() and all(Path(d).stat().st_mtime <= out.stat().st_mtime for d in deps):
+        return
+    tmp = out.with_name(f"{out.name}.{os.getpid()}")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(tmp), *map(str, srcs),
+           "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle"),
+           "-L", str(lib_dir), "-lpairalign_b200", "-Wl,-rpath," + str(lib_dir), *extra]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    os.replace(tmp, out)
 
 
 @pytest.fixture(scope="module")
@@ -29,10 +43,7 @@ def exe():
     srcs = [HOST / "pairalign_main.cpp", HOST / "fasta_index.cpp", HOST / "mad_groups.cpp", HOST / "seqpair_batch.cpp",
             ROOT / "tests" / "host_double" / "seqpair_batch_oracle.cpp"]
     assert not any(s.name == "seqpair_batch_device.cpp" for s in srcs)
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(out), *map(str, srcs),
-           "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle"),
-           "-L", str(build.LIB_DIR), "-lpairalign_b200", "-Wl,-rpath," + str(build.LIB_DIR), "-lpthread"]
-    subprocess.run(cmd, check=True, cwd=ROOT)
+    _compile(out, srcs + sorted(HOST.glob("*.h")), srcs, build.LIB_DIR, ["-lpthread"])
     return out
 
 
@@ -84,10 +95,7 @@ def nj_exe():
     out = ROOT / "build" / "treeator_hosttest"
     out.parent.mkdir(exist_ok=True)
     srcs = [ROOT / "phylommand_b200" / "host_nj" / "treeator_nj_main.cpp", ROOT / "tests" / "host_double" / "nj_build_oracle.cpp"]
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-o", str(out), *map(str, srcs),
-           "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle"),
-           "-L", str(build.LIB_DIR), "-lpairalign_b200", "-Wl,-rpath," + str(build.LIB_DIR)]
-    subprocess.run(cmd, check=True, cwd=ROOT)
+    _compile(out, srcs, srcs, build.LIB_DIR, [])
     return out
 
 
