@@ -213,3 +213,65 @@ def test_odd_headers_and_group_arguments_against_the_reference(exe, tmp_path, se
         assert ours[0] == ref[0], (flags, seed)
         assert ours[1] == ref[1], (flags, seed)
         assert ours[2] == ref[2], (flags, seed)
+
+
+# ---- treeator -n: reader, neighbour joining (oracle) and printer against the reference's treeator ------------------------
+REF_TREEATOR = ROOT / "oracle" / "_ref" / "treeator"
+
+
+def make_matrix(seed):
+    """A triangular matrix as pairalign -m prints it, with the liberties a hand-made file takes: tabs and runs of
+    blanks, CRLF, values in scientific notation, -0 / inf / nan, integer ties, labels alone on a line."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(3, 14))
+    style = int(rng.integers(0, 4))
+    labels = bool(seed % 4)
+    pts = rng.random((n, 3))
+    rows = []
+    for a in range(n - 1):
+        vals = []
+        for b in range(a + 1, n):
+            d = float(np.linalg.norm(pts[a] - pts[b]))
+            if style == 1:
+                d = float(int(d * 4))                       # many exact ties
+            txt = f"{d:.6g}"
+            u = rng.random()
+            if style == 2 and u < 0.1:
+                txt = f"{d:.3e}"
+            elif style == 3 and u < 0.06:
+                txt = ["-0", "inf", "nan", "0"][int(rng.integers(4))]
+            vals.append(txt)
+        sep = "\t" if rng.random() < 0.2 else " " * int(rng.integers(1, 3))
+        row = (f"t{a:02d}" + sep if labels else "") + " " * a + sep.join(vals) + " "
+        if labels and rng.random() < 0.1:
+            row = f"t{a:02d}\n" + " " * a + sep.join(vals) + " "        # the label alone on its line
+        rows.append(row)
+    eol = "\r\n" if seed % 9 == 0 else "\n"
+    text = eol.join(rows) + eol
+    if labels or rng.random() < 0.5:
+        text += (f"t{n - 1:02d}" if labels else str(n - 1)) + eol      # pairalign prints the last name with or without -n
+    return text, labels
+
+
+@pytest.mark.skipif(not REF_TREEATOR.exists(), reason="the compiled reference treeator is not here")
+@pytest.mark.parametrize("seed", range(60))
+def test_treeator_host_side_against_the_reference(tmp_path, seed):
+    from tests.test_host_replay_cpu import _compile
+    from phylommand_b200 import build
+    from tests import oracle_lib
+    build.build_library()
+    oracle_lib.load()
+    out = ROOT / "build" / "treeator_hosttest"
+    srcs = [ROOT / "phylommand_b200" / "host_nj" / "treeator_nj_main.cpp", ROOT / "tests" / "host_double" / "nj_build_oracle.cpp"]
+    _compile(out, srcs, srcs, build.LIB_DIR, [])
+    text, labels = make_matrix(7000 + seed)
+    (tmp_path / "m.txt").write_bytes(text.encode())
+    for flags in (["-n"], ["-n", "-0"]):
+        flags = flags + ([] if labels else ["-L"])
+        ref = subprocess.run([str(REF_TREEATOR), *flags, "m.txt"], cwd=tmp_path, capture_output=True, timeout=120)
+        ours = subprocess.run([str(out), *flags, "m.txt"], cwd=tmp_path, capture_output=True, timeout=120)
+        if b"nan" in ref.stdout:                     # x86 prints inf - inf as -nan: the documented sign-of-NaN deviation
+            assert ours.stdout.replace(b"-nan", b"nan") == ref.stdout.replace(b"-nan", b"nan"), (flags, seed)
+        else:
+            assert ours.stdout == ref.stdout, (flags, seed)
+        assert ours.returncode == ref.returncode, (flags, seed)
