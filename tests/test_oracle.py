@@ -117,6 +117,45 @@ def test_oracle_against_live_reference(oracle):
         assert oracle.similarity(int(r["dist"]), int(r["len"])) == want["sim"]
 
 
+def test_oracle_against_live_reference_structured(oracle):
+    """Inputs where ties decide everything: repeats and homopolymers, one sequence inside the other, overlapping ends,
+    nothing but ambiguity codes, one to four bases with gap characters (4 000 such pairs were run once: no difference)."""
+    ref = oracle_lib.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here (the golden vectors above are the committed pin)")
+    rng = np.random.default_rng(2024)
+    alph, amb = "ACGT", "RYSWKMBDHVN"
+    rnd = lambda n, letters=alph: "".join(letters[int(k)] for k in rng.integers(0, len(letters), size=n))
+    for trial in range(500):
+        kind = trial % 5
+        if kind == 0:
+            unit = rnd(int(rng.integers(1, 4)))
+            tx, ty = "N" + unit * int(rng.integers(1, 40)), "N" + unit * int(rng.integers(1, 40))
+            if rng.random() < 0.5:
+                ty = ty[:-1] + rnd(1)
+        elif kind == 1:
+            a = rnd(int(rng.integers(20, 150)))
+            i = int(rng.integers(0, len(a) - 3)); j = int(rng.integers(i + 2, len(a)))
+            tx, ty = "N" + a, "N" + a[i:j]
+            if rng.random() < 0.5:
+                tx, ty = ty, tx
+        elif kind == 2:
+            a = rnd(120)
+            k1 = int(rng.integers(10, 110))
+            tx, ty = "N" + a[:k1 + int(rng.integers(0, 10))], "N" + a[k1 - int(rng.integers(0, 10)):]
+        elif kind == 3:
+            tx, ty = "N" + rnd(int(rng.integers(1, 60)), amb + alph), "N" + rnd(int(rng.integers(1, 60)), amb + alph)
+        else:
+            tx, ty = "N" + rnd(int(rng.integers(1, 5))), "n" + rnd(int(rng.integers(1, 5)), "acgt-")
+        want = ref.run(tx, ty)
+        x, y = oracle.encode(tx), oracle.encode(ty)
+        r, ax, ay = oracle.align_full(x, y)
+        assert int(r["score"]) == want["score"] and int(r["dist"]) == want["hamming"], (tx, ty)
+        assert oracle.decode(ax) == want["x"] and oracle.decode(ay) == want["y"], (tx, ty)
+        assert oracle.similarity(int(r["dist"]), int(r["len"])) == want["sim"], (tx, ty)
+        assert tuple(r) == tuple(oracle.align_forward(x, y)), (tx, ty)
+
+
 def test_all_pairs_driver_order(oracle):
     _, seqs = synth.make_random(7, 3, 5, 40)
     enc = [synth.to_masks(s) for s in seqs]
