@@ -244,6 +244,73 @@ int pa_oracle_align_forward(const uint8_t *x, int32_t n, const uint8_t *y, int32
     return 0;
 }
 
+/* pa_oracle_align_ops for pairs whose three full matrices do not fit (30 kb x 30 kb: 10.8 GB): the forward-only
+ * recurrence above with the move of every cell kept in 2 bits (225 MB for such a pair), then the reference's walk
+ * (src/seqpair.cpp:146-178) over the moves.  Checked against pa_oracle_align_ops on small pairs (tests/test_oracle.py);
+ * it exists so that the op strings of the CUDA path can be compared exactly at BASELINE.json config 5 sizes. */
+int pa_oracle_align_ops_compact(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                                int32_t match, int32_t mismatch, int32_t GO, int32_t GE,
+                                pa_oracle_result *res, uint8_t *ops_out, int32_t *alen_out) {
+    if (n <= 0 || m <= 0 || !res || !ops_out) return -1;
+    const size_t row_bytes = ((size_t)m + 3) / 4;
+    uint8_t *mv = (uint8_t *)calloc((size_t)n * row_bytes, 1);      /* 0 D, 1 U, 2 L */
+    int32_t *A = (int32_t *)calloc((size_t)m, sizeof(int32_t));
+    int32_t *Gy = (int32_t *)calloc((size_t)m, sizeof(int32_t));
+    if (!mv || !A || !Gy) { free(mv); free(A); free(Gy); return -1; }
+    int32_t best = INT_MIN, bi = n - 1, bj = m - 1;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t diagA = 0, leftGx = 0;
+        uint8_t *row = mv + (size_t)i * row_bytes;
+        for (int32_t j = 0; j < m; ++j) {
+            int32_t c = pa_oracle_cost(x[i], y[j], match, mismatch);
+            int32_t upA = A[j], upGy = Gy[j];
+            int32_t a, gy, gx;
+            if (i == 0 || j == 0) {
+                if (i == 0 && j == 0) a = c;
+                else if (i == 0) a = wadd(leftGx, c);
+                else a = wadd(upGy, c);
+                gy = 0; gx = 0;
+            } else {
+                int32_t mx = diagA;
+                if (upGy > mx) mx = upGy;
+                if (leftGx > mx) mx = leftGx;
+                a = wadd(mx, c);
+                int32_t open = wadd(diagA, GO);
+                int32_t uy = wadd(upGy, GE), lx = wadd(leftGx, GE);
+                gy = (open > uy) ? open : uy;
+                gx = (open > lx) ? open : lx;
+            }
+            unsigned move = (a >= gy && a >= gx) ? 0u : (gy >= gx ? 1u : 2u);
+            row[j >> 2] |= (uint8_t)(move << ((j & 3) * 2));
+            diagA = upA;
+            A[j] = a; Gy[j] = gy;
+            leftGx = gx;
+            if (j == m - 1 && a > best) { best = a; bi = i; bj = j; }
+        }
+    }
+    for (int32_t j = 0; j < m; ++j)
+        if (A[j] > best) { best = A[j]; bi = n - 1; bj = j; }
+    res->score = best; res->end_i = bi; res->end_j = bj;
+    int32_t i = bi, j = bj, k = 0;
+    uint32_t d = 0, l = 0;
+    if (i < n - 1) { for (int32_t pos = n - 1; pos > i; --pos) ops_out[k++] = 1; }
+    else if (j < m - 1) { for (int32_t pos = m - 1; pos > j; --pos) ops_out[k++] = 2; }
+    while (i >= 0 || j >= 0) {
+        unsigned move = 3;
+        if (i >= 0 && j >= 0) move = (mv[(size_t)i * row_bytes + (size_t)(j >> 2)] >> ((j & 3) * 2)) & 3u;
+        if (move == 0) {
+            if (x[i] != 0 && y[j] != 0) { ++l; if ((x[i] & y[j]) == 0) ++d; }
+            ops_out[k++] = 0; --i; --j;
+        } else if (j < 0 || (i >= 0 && move == 1)) { ops_out[k++] = 1; --i; }
+        else { ops_out[k++] = 2; --j; }
+    }
+    for (int32_t a = 0, b = k - 1; a < b; ++a, --b) { uint8_t t = ops_out[a]; ops_out[a] = ops_out[b]; ops_out[b] = t; }
+    res->dist = d; res->len = l;
+    if (alen_out) *alen_out = k;
+    free(mv); free(A); free(Gy);
+    return 0;
+}
+
 void pa_oracle_aligned_stats(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
                              pa_oracle_result *res) {
     int32_t k = n < m ? n : m;                   /* src/seqpair.cpp:239,259 */

@@ -71,6 +71,12 @@ int pa_oracle_align_ops(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m
                         int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
                         pa_oracle_result *res, uint8_t *ops, int32_t *alen);
 
+/* The same op string from a forward pass that keeps 2 bits per cell instead of three int matrices: for pairs of
+ * tens of kilobases (30 kb x 30 kb: 225 MB). */
+int pa_oracle_align_ops_compact(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
+                                int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
+                                pa_oracle_result *res, uint8_t *ops, int32_t *alen);
+
 int pa_oracle_align_forward(const uint8_t *x, int32_t n, const uint8_t *y, int32_t m,
                             int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
                             pa_oracle_result *res);

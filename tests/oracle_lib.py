@@ -38,6 +38,11 @@ class Oracle:
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        for name in ("pa_oracle_align_ops", "pa_oracle_align_ops_compact"):
+            f = getattr(lib, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                          C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         lib.pa_oracle_align_forward.restype = C.c_int
         lib.pa_oracle_align_forward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                 C.c_int32, C.c_int32, C.c_void_p]
@@ -88,6 +93,19 @@ class Oracle:
                                            res.ctypes.data, ax.ctypes.data, ay.ctypes.data, C.byref(alen))
         assert rc == 0
         return res[0], ax[:alen.value].copy(), ay[:alen.value].copy()
+
+    def align_ops(self, x, y, match=7, mismatch=-5, go=-15, ge=-1, compact=False):
+        """(record, op string): 0 = x over y, 1 = x over a gap, 2 = a gap over y.  compact: 2 bits per cell instead of
+        the three full matrices (long pairs)."""
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        ops = np.empty(len(x) + len(y) + 1, dtype=np.uint8)
+        alen = C.c_int32(0)
+        f = self.lib.pa_oracle_align_ops_compact if compact else self.lib.pa_oracle_align_ops
+        rc = f(x.ctypes.data, len(x), y.ctypes.data, len(y), match, mismatch, go, ge, res.ctypes.data, ops.ctypes.data, C.byref(alen))
+        assert rc == 0
+        return res[0], ops[:alen.value].copy()
 
     def align_forward(self, x, y, match=7, mismatch=-5, go=-15, ge=-1):
         x = np.ascontiguousarray(x, dtype=np.uint8)

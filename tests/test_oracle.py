@@ -156,6 +156,32 @@ def test_oracle_against_live_reference_structured(oracle):
         assert tuple(r) == tuple(oracle.align_forward(x, y)), (tx, ty)
 
 
+def test_compact_op_strings_equal_the_literal_ones(oracle):
+    """pa_oracle_align_ops_compact (2-bit moves, for 30 kb pairs) against the full-matrix walk: same record, same ops,
+    and the ops render to the gapped strings of align_full."""
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        kind = trial % 3
+        _, seqs = synth.make_random(2, int(rng.integers(1 << 30)), 1, 150,
+                                    iupac=0.05 if kind else 0.0, gaps=0.12 if kind == 2 else 0.0, related=bool(trial % 2))
+        x = oracle.encode("N" + synth.to_text(seqs[0]))
+        y = oracle.encode("N" + synth.to_text(seqs[1]))
+        if len(x) == 0 or len(y) == 0:
+            continue
+        r_full, ax, ay = oracle.align_full(x, y)
+        r1, ops1 = oracle.align_ops(x, y)
+        r2, ops2 = oracle.align_ops(x, y, compact=True)
+        assert tuple(r1) == tuple(r_full) == tuple(r2)
+        assert ops1.tolist() == ops2.tolist()
+        i = j = 0
+        for k, o in enumerate(ops1):
+            assert (int(ax[k]) if o != 2 else 0) == (int(x[i]) if o != 2 else 0)
+            assert (int(ay[k]) if o != 1 else 0) == (int(y[j]) if o != 1 else 0)
+            i += o != 2
+            j += o != 1
+        assert i == len(x) and j == len(y) and len(ax) == len(ops1)
+
+
 def test_all_pairs_driver_order(oracle):
     _, seqs = synth.make_random(7, 3, 5, 40)
     enc = [synth.to_masks(s) for s in seqs]
