@@ -188,6 +188,12 @@ uint64_t pa_count_cells(uint64_t first, uint64_t count);
 
 int pa_get_timing(pa_timing *t);
 
+/* Device-free: the longest sequence the s16x2 kernel takes with plain 16-bit scores for these parameters
+ * (longer A/C/G/T pairs use its floating-window form or the int32 kernels) and the bias it stores states with
+ * (stored = true + bias; both 16-bit halves stay negative).  0 / 0 when the parameters
+ * are outside the byte-table range (general kernel). */
+int pa_s16_limits(const pa_params *params, uint32_t *max_len, int32_t *bias);
+
 /* ---- per-pair statistics (host; the reference's exact expressions) -------- */
 
 /* similarity(false): len>0 ? 1.0-(dist/double(len)) : 1.0  (src/seqpair.cpp:272-273) */

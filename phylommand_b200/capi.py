@@ -58,6 +58,7 @@ SYMBOLS = {
     "pa_partition_pairs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "pa_partition_by_length": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pa_count_cells": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "pa_s16_limits": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "pa_get_timing": (C.c_int, [C.POINTER(PaTiming)]),
     "pa_similarity": (C.c_double, [C.c_uint32, C.c_uint32]),
     "pa_pdistance": (C.c_double, [C.c_uint32, C.c_uint32]),
@@ -210,6 +211,14 @@ def align_pairs_ops(ia, ib, lengths, **params):
     _check(load().pa_align_pairs_ops(C.byref(p), ia.ctypes.data, ib.ctypes.data, len(ia), ops.ctypes.data, cap,
                                      offsets.ctypes.data, n_ops.ctypes.data, res.ctypes.data))
     return ops, offsets, n_ops, res
+
+
+def s16_limits(**params):
+    """(longest sequence with plain 16-bit scores, storage bias) of the s16x2 kernel for these scoring parameters."""
+    p = make_params(**params)
+    max_len, bias = C.c_uint32(0), C.c_int32(0)
+    _check(load().pa_s16_limits(C.byref(p), C.byref(max_len), C.byref(bias)))
+    return max_len.value, bias.value
 
 
 def partition_pairs(first: int, count: int, n_parts: int) -> np.ndarray:

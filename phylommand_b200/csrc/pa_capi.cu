@@ -1149,6 +1149,16 @@ int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b, uin
     return PA_OK;
 }
 
+int pa_s16_limits(const pa_params *params, uint32_t *max_len, int32_t *bias) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    int b = 0;
+    const uint32_t l = fast_params_ok(*params) ? max_len16(*params, &b) : 0;
+    if (max_len) *max_len = l;
+    if (bias) *bias = l ? b : 0;
+    return PA_OK;
+}
+
 int pa_get_timing(pa_timing *t) {
     if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
     if (!t) return fail(PA_EINVAL, "NULL timing");

@@ -63,3 +63,48 @@ def test_stats_match_oracle_bitwise(capi, oracle):
                              (capi.jc_distance, oracle.jc), (capi.jc_minus_p, oracle.diff)):
             a, b = mine(d, l), theirs(d, l)
             assert (math.isnan(a) and math.isnan(b)) or a.hex() == b.hex(), (d, l)
+
+
+def test_s16_storage_bias_keeps_every_state_negative_and_in_range(capi):
+    """The s16x2 kernel stores states as true value + bias so that H + GO can be a plain 32-bit add.
+    True values lie in [-(|ge| L + |mismatch| + |go|), match L] (checked against the literal DP in the test below);
+    with the bias both ends must stay negative, and one more gap extension must still fit int16."""
+    for sc in (dict(), dict(match=5, mismatch=-4, gap_open=-10, gap_ext=-2), dict(match=20, mismatch=-25, gap_open=-100, gap_ext=-7),
+               dict(match=1, mismatch=-1, gap_open=0, gap_ext=0), dict(match=127, mismatch=-1, gap_open=-127, gap_ext=-50)):
+        p = dict(capi.DEFAULT_PARAMS); p.update(sc)
+        L, bias = capi.s16_limits(**sc)
+        assert L >= 16 and bias < 0, sc
+        top = max(p["match"], 1) * L + bias
+        bottom = bias - (max(-p["gap_ext"], 1) * (L + 1) + abs(p["mismatch"]) + abs(p["gap_open"]))
+        assert top <= -16 and bottom >= -32768, (sc, L, bias, top, bottom)
+    assert capi.s16_limits() == (4059, -16 - 7 * 4059)
+    assert capi.s16_limits(match=1000) == (0, 0)            # outside the byte tables: general kernel
+    assert capi.s16_limits(match=127, mismatch=-128, gap_open=-127) == (0, 0)      # mismatch + gap_open does not fit a byte
+
+
+def test_true_value_range_of_the_recurrence(oracle):
+    """The bound the bias rests on, on the literal recurrence: no state (nor H + GO, nor a gap state + GE) ever leaves
+    [-(L + 20), 7 L] for pairalign's scoring, including the inputs built to go low (nothing matches) or high (identical)."""
+    rng = np.random.default_rng(5)
+    M, X, GO, GE = 7, -5, -15, -1
+    cases = [(np.zeros(70, int), np.ones(70, int)), (np.zeros(70, int), np.zeros(70, int)), (np.arange(70) % 2, (np.arange(70) + 1) % 2),
+             (np.zeros(3, int), np.ones(70, int)), (np.ones(70, int), np.zeros(3, int))]
+    cases += [(rng.integers(0, 4, int(rng.integers(1, 60))), rng.integers(0, 2, int(rng.integers(1, 60)))) for _ in range(25)]
+    for x, y in cases:
+        n, m = len(x), len(y)
+        H = np.zeros((n, m), int); Gy = np.zeros((n, m), int); Gx = np.zeros((n, m), int)
+        lo, hi = 0, 0
+        for i in range(n):
+            for j in range(m):
+                s = M if x[i] == y[j] else X
+                if i == 0 or j == 0:
+                    H[i, j] = s
+                else:
+                    o = H[i - 1, j - 1] + GO
+                    u, l = Gy[i - 1, j] + GE, Gx[i, j - 1] + GE
+                    H[i, j] = max(H[i - 1, j - 1], Gy[i - 1, j], Gx[i, j - 1]) + s
+                    Gy[i, j], Gx[i, j] = max(o, u), max(o, l)
+                    lo = min(lo, o, u, l)
+                lo, hi = min(lo, H[i, j]), max(hi, H[i, j], Gy[i, j], Gx[i, j])
+        L = max(n, m)
+        assert lo >= -(L + 20) and hi <= 7 * L, (lo, hi, L)
