@@ -4,13 +4,16 @@ what they find, then drop the switch).
 
   * the differential fuzz of tests/test_host_fuzz_vs_reference.py through the real command line (CUDA module)
     against the reference binary that travels in oracle/_ref/;
-  * CUDA vs oracle on inputs where ties decide everything (repeats, containment, overlapping ends, all-ambiguous)."""
+  * CUDA vs oracle on inputs where ties decide everything (repeats, containment, overlapping ends, all-ambiguous);
+  * the op strings of two 30 kb pairs against the oracle's 2-bit-move walk (exact parity of -a at config 5 size)."""
 import os
 import subprocess
 from pathlib import Path
 
 import numpy as np
 import pytest
+
+from phylommand_b200 import synth
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PAIRALIGN_EXTENDED") != "1", reason="not yet validated on a GPU (PAIRALIGN_EXTENDED=1 runs them)")]
@@ -72,3 +75,20 @@ def test_structured_inputs_on_every_kernel(gpu, oracle):
     masks, offsets = gpu.pack(enc)
     want = oracle.all_pairs(masks, offsets, threads=8)
     assert got.tobytes() == want.tobytes()
+
+
+def test_alignments_of_30kb_pairs_equal_the_oracle(gpu, oracle):
+    """BASELINE.json config 5 size, exactly: the op strings of two 30 kb pairs (CTA-per-pair kernel with stored moves,
+    warp-per-pair walk) against the oracle's walk over its own 2-bit moves (pa_oracle_align_ops_compact, which
+    tests/test_oracle.py ties to the reference-literal full-matrix walk on small pairs).  About 20 s of CPU."""
+    _, seqs = synth.make_long(3, 1006, length=30000, spread=0.05)
+    enc = [synth.to_masks(s) for s in seqs]
+    gpu.upload(enc)
+    ia, ib = np.array([0, 2]), np.array([1, 0])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    for k in range(len(ia)):
+        r, want = oracle.align_ops(enc[ia[k]], enc[ib[k]], compact=True)
+        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
+        got = ops[int(off[k]):int(off[k]) + int(n_ops[k])]
+        assert got.tobytes() == want.tobytes(), (ia[k], ib[k])

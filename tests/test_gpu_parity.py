@@ -482,20 +482,3 @@ def test_alignments_at_config5_size_are_consistent(gpu):
         # the walk starts at the end cell: no compared column lies beyond it
         last = int(np.flatnonzero(both)[-1])
         assert xi[last] <= int(res[k]["end_i"]) and yj[last] <= int(res[k]["end_j"])
-
-
-def test_alignments_of_30kb_pairs_equal_the_oracle(gpu, oracle):
-    """BASELINE.json config 5 size, exactly: the op strings of two 30 kb pairs (CTA-per-pair kernel with stored moves,
-    warp-per-pair walk) against the oracle's walk over its own 2-bit moves (pa_oracle_align_ops_compact, which
-    tests/test_oracle.py ties to the reference-literal full-matrix walk on small pairs).  About 20 s of CPU."""
-    _, seqs = synth.make_long(3, 1006, length=30000, spread=0.05)
-    enc = [synth.to_masks(s) for s in seqs]
-    gpu.upload(enc)
-    ia, ib = np.array([0, 2]), np.array([1, 0])
-    lens = np.array([len(e) for e in enc])
-    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
-    for k in range(len(ia)):
-        r, want = oracle.align_ops(enc[ia[k]], enc[ib[k]], compact=True)
-        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
-        got = ops[int(off[k]):int(off[k]) + int(n_ops[k])]
-        assert got.tobytes() == want.tobytes(), (ia[k], ib[k])
