@@ -275,3 +275,34 @@ def test_treeator_host_side_against_the_reference(tmp_path, seed):
         else:
             assert ours.stdout == ref.stdout, (flags, seed)
         assert ours.returncode == ref.returncode, (flags, seed)
+
+
+LONG_AND_ERRORS = [["--jc_distance", "--names", "--matrix"], ["--distances", "--names"], ["--proportion_difference", "--matrix"],
+                   ["--similarity"], ["--difference", "--names", "--matrix"], ["--alignments", "--names"], ["--aligned", "--jc_distance"],
+                   ["--group", "both:cut-off=0.9"], ["--group", "alignment_groups", "--verbose"], ["-j", "-n", "-m", "-v"],
+                   ["--format", "fasta", "-j"], ["--format", "pairfa", "-j"], ["-h"], ["--help"], ["-j", "-x"], ["--format", "xml"],
+                   ["-g", "nonsense"], ["-g", "both:foo=1"], ["-g"]]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_long_options_stdin_and_argument_errors_against_the_reference(exe, tmp_path, seed):  # noqa: F811
+    """Long option names, input on stdin (the alignment groups then go to sequence.alignment_groups), help, and
+    the argument errors with their exit codes.  (-T/--threads is left out on purpose: only the reference's PTHREAD
+    build knows it; here it is accepted and ignored.)"""
+    text = make_case(5000 + seed, group=(seed % 2 == 0))
+    for flags in LONG_AND_ERRORS:
+        for use_stdin in (False, True):
+            outs = []
+            for binary, sub in ((REF, "ref"), (exe, "ours")):
+                d = tmp_path / f"{sub}_{int(use_stdin)}"
+                d.mkdir(exist_ok=True)
+                for old in d.iterdir():
+                    old.unlink()
+                (d / "in.fst").write_text(text)
+                if use_stdin:
+                    r = subprocess.run([str(binary), *flags], cwd=d, input=text.encode(), capture_output=True, timeout=120)
+                else:
+                    r = subprocess.run([str(binary), *flags, "in.fst"], cwd=d, capture_output=True, timeout=120)
+                made = sorted((p.name, p.read_bytes()) for p in d.iterdir() if p.name != "in.fst")
+                outs.append((r.returncode, r.stdout, made))
+            assert outs[0] == outs[1], (flags, use_stdin, seed)
