@@ -84,3 +84,25 @@ def test_partition_by_length_edge_cases(capi):
         capi.partition_by_length(lens, 8, 5, 2)
     b, c = capi.partition_by_length(np.array([5], dtype=np.uint32), 0, 0, 2)   # a single sequence has no pairs
     assert b.tolist() == [0, 0, 0]
+
+
+def test_partition_by_length_properties(capi):
+    """Random length sets, sub-ranges and part counts: the parts tile the range in order, their cells add up to the
+    cells of the range (recounted pair by pair), and no part exceeds the ideal share by more than one pair's cells."""
+    rng = np.random.default_rng(12)
+    for trial in range(200):
+        n = int(rng.integers(2, 60))
+        lens = rng.integers(0 if trial % 5 == 0 else 1, 3000, size=n).astype(np.uint32)
+        total = n * (n - 1) // 2
+        first = int(rng.integers(0, total + 1))
+        count = int(rng.integers(0, total - first + 1))
+        parts = int(rng.integers(1, 12))
+        b, c = capi.partition_by_length(lens, first, count, parts)
+        b = b.astype(np.int64)
+        assert b[0] == first and b[-1] == first + count and np.all(np.diff(b) >= 0)
+        pair_cells = np.array([int(lens[x]) * int(lens[y]) for x in range(n) for y in range(x + 1, n)], dtype=np.int64)
+        want = [int(pair_cells[b[p]:b[p + 1]].sum()) for p in range(parts)]
+        assert [int(v) for v in c] == want
+        whole = int(pair_cells[first:first + count].sum())
+        biggest = int(pair_cells[first:first + count].max()) if count else 0
+        assert max(want) <= whole / parts + biggest + 1
