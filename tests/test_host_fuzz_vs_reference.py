@@ -306,3 +306,26 @@ def test_long_options_stdin_and_argument_errors_against_the_reference(exe, tmp_p
                 made = sorted((p.name, p.read_bytes()) for p in d.iterdir() if p.name != "in.fst")
                 outs.append((r.returncode, r.stdout, made))
             assert outs[0] == outs[1], (flags, use_stdin, seed)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_verbose_stderr_against_the_reference(exe, tmp_path, seed):  # noqa: F811
+    """-v: the progress dots, the messages and the approximate MAD of the whole group on stderr (840 such runs were
+    compared once: no difference).  The program path and the two time stamps are masked."""
+    import re
+    group = seed % 2 == 0
+    (tmp_path / "in.fst").write_text(make_case(6000 + seed, group))
+
+    def norm(raw, path):
+        text = raw.decode(errors="replace").replace(str(path), "BIN")
+        return re.sub(r"(Sat|Sun|Mon|Tue|Wed|Thu|Fri) \w{3} +\d+ [\d:]+ \d{4}", "DATE", text)
+
+    for flags in (GROUP_MODES if group else MODES[:5]) + [["-g", "alignment_groups"]]:
+        outs = []
+        for binary, sub in ((REF, "ref"), (exe, "ours")):
+            d = tmp_path / sub
+            d.mkdir(exist_ok=True)
+            (d / "in.fst").write_bytes((tmp_path / "in.fst").read_bytes())
+            r = subprocess.run([str(binary), *flags, "-v", "in.fst"], cwd=d, capture_output=True, timeout=120)
+            outs.append((r.returncode, r.stdout, norm(r.stderr, binary)))
+        assert outs[0] == outs[1], (flags, seed)
