@@ -53,6 +53,9 @@ struct Device {
     // sequence store
     uint32_t *p2 = nullptr, *p4 = nullptr, *off2 = nullptr, *off4 = nullptr, *len = nullptr;
     uint8_t *pure = nullptr;
+    uint8_t *raw = nullptr;                   // the uploaded 4-bit sets, one per byte: input of pa_pack_kernel only
+    unsigned long long *raw_off = nullptr;    // their offsets (n_seq + 1)
+    size_t cap_raw = 0, cap_raw_off = 0;
     // scratch
     unsigned long long *counters = nullptr;   // [0] fast work counter, [1] general work counter
     unsigned int *n_deferred = nullptr;       // [0] deferred by the s16x2 kernel, [1] non-A/C/G/T, [2] long pairs
@@ -78,12 +81,15 @@ struct Device {
     uint32_t *d_nops = nullptr;
     pa_pair_result *d_res = nullptr;
     size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0;
-    cudaEvent_t ev[6] = {};
-    cudaEvent_t ev_done[2] = {};
-    bool chunk_duo = false, chunk_fast = false, chunk_gen = false;   // which DP kernels the last chunk launched
-    cudaEvent_t ev_mid = nullptr;                 // between the s16x2 kernel and the 32-bit follow-up
-    cudaEvent_t ev_cta = nullptr;                 // after the CTA-per-pair kernel
-    bool chunk_cta = false;
+    // Events of one in-flight chunk (two chunks are in flight: slot = chunk & 1).  k[0]..k[1] s16x2 stage,
+    // k[1]..k[2] 32-bit warp stage, k[2]..k[3] CTA-per-pair stage, k[3]..k[4] general stage; k[4] also releases the
+    // D2H copy of the chunk on copy_stream, `done` marks its end (and lets the next kernel reuse d_out[slot]).
+    struct ChunkEvents {
+        cudaEvent_t k[5] = {};
+        cudaEvent_t done = nullptr;
+        bool duo = false, fast = false, cta = false, gen = false;   // which DP kernels the chunk launched
+    } ce[2];
+    cudaEvent_t ev[6] = {};                       // pa_align_pairs_ops, pair-list upload
     double cta_ms = 0;
     // timing accumulators of the last call
     double duo_ms = 0, fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
@@ -139,8 +145,9 @@ struct Context {
     uint32_t n_seq = 0;
     std::vector<uint32_t> len;
     Triangle tri;
-    std::vector<uint8_t> host_masks;       // the uploaded 4-bit sets (pa_align_pair_traceback rebuilds strings from them)
-    std::vector<uint64_t> host_offsets;
+    uint8_t *host_masks = nullptr;         // the uploaded 4-bit sets, pinned: the devices pack from them (pa_pack_kernel)
+    uint64_t host_masks_cap = 0;           // and pa_align_pair_traceback rebuilds strings from them
+    std::vector<unsigned long long> host_offsets;     // offsets into host_masks (n_seq + 1)
     std::vector<uint8_t> host_pure;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
@@ -170,14 +177,12 @@ void free_device(Device &d) {
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
     cudaFree(d.fastok); cudaFree(d.exc); cudaFree(d.exc_off);
     cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3); cudaFree(d.bbuf);
-    cudaFree(d.row_items);
-    if (d.ev_mid) cudaEventDestroy(d.ev_mid);
-    if (d.ev_cta) cudaEventDestroy(d.ev_cta);
+    cudaFree(d.row_items); cudaFree(d.raw); cudaFree(d.raw_off);
+    for (auto &c : d.ce) { for (auto &e : c.k) if (e) cudaEventDestroy(e); if (c.done) cudaEventDestroy(c.done); }
     for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
     cudaFree(d.d_ia); cudaFree(d.d_ib);
     cudaFree(d.d_dirs); cudaFree(d.d_ops); cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
     for (auto &e : d.ev) if (e) cudaEventDestroy(e);
-    for (auto &e : d.ev_done) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     d = Device();
@@ -268,6 +273,45 @@ pa_general_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, c
     }
 }
 
+// Packing on the device (pa_upload_sequences): one CTA per sequence, one thread per 16 bases -> one 2-bit word
+// (A0 G1 C2 T3, placeholder 0 for anything else) and two 4-bit words; every word of the sequence's 16-byte-aligned
+// slot is written, so nothing has to be cleared first.  pure[s] = every set of s has exactly one bit.
+__global__ void __launch_bounds__(128)
+pa_pack_kernel(const uint8_t *raw, const unsigned long long *raw_off, const uint32_t *len, const uint32_t *off2,
+               const uint32_t *off4, const uint32_t n_seq, uint32_t *p2, uint32_t *p4, uint8_t *pure) {
+    __shared__ int s_bad;
+    for (uint32_t s = blockIdx.x; s < n_seq; s += gridDim.x) {
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        const uint32_t L = len[s];
+        const uint8_t *src = raw + raw_off[s];
+        const uint32_t n2 = ((L + 15) / 16 + 3) / 4 * 4, n4 = ((L + 7) / 8 + 3) / 4 * 4;
+        uint32_t *o2 = p2 + off2[s], *o4 = p4 + off4[s];
+        int bad = 0;
+        for (uint32_t u = threadIdx.x; u < n2 || 2 * u < n4; u += blockDim.x) {
+            uint32_t w2 = 0, w4lo = 0, w4hi = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t pos = u * 16 + k;
+                if (pos < L) {
+                    const uint32_t v = src[pos] & 15u;
+                    const uint32_t code = (v == 2) ? 1u : (v == 4) ? 2u : (v == 8) ? 3u : 0u;
+                    bad |= (v != 1 && v != 2 && v != 4 && v != 8);
+                    w2 |= code << (2 * k);
+                    if (k < 8) w4lo |= v << (4 * k); else w4hi |= v << (4 * (k - 8));
+                }
+            }
+            if (u < n2) o2[u] = w2;
+            if (2 * u < n4) o4[2 * u] = w4lo;
+            if (2 * u + 1 < n4) o4[2 * u + 1] = w4hi;
+        }
+        if (bad) s_bad = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) pure[s] = s_bad ? 0 : 1;
+        __syncthreads();
+    }
+}
+
 // item (pair of pairs) that holds triangle index q
 uint64_t item_of(const Context &c, uint64_t q) {
     uint32_t a, b;
@@ -284,24 +328,20 @@ uint64_t item_of(const Context &c, uint64_t q) {
 //   3. general kernel                         IUPAC sets, '-', any scoring parameters
 // Events: ev[0]..ev[1] stage 1, ev[1]..ev_mid stage 2, ev[2]..ev[3] stage 3.
 int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
-                 const uint32_t *d_ia, const uint32_t *d_ib, pa_pair_result *d_out) {
+                 const uint32_t *d_ia, const uint32_t *d_ib, pa_pair_result *d_out, Device::ChunkEvents &E) {
     const SeqStore S = store_of(d, c.n_seq);
     Scoring sc{p.match, p.mismatch, p.gap_open, p.gap_ext};
     PairSource src{first, d_ia, d_ib, nullptr};
     CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
     CU(cudaMemsetAsync(d.n_deferred, 0, 3 * sizeof(unsigned int), d.stream));
-    d.chunk_duo = d.chunk_fast = d.chunk_cta = d.chunk_gen = false;
+    E.duo = E.fast = E.cta = E.gen = false;
     const int threads = WARPS_PER_CTA * 32;
     if (p.aligned) {
-        d.chunk_duo = true;
-        CU(cudaEventRecord(d.ev[0], d.stream));
+        E.duo = true;
+        CU(cudaEventRecord(E.k[0], d.stream));
         pa_aligned_stats_kernel<<<d.grid_stats, threads, 0, d.stream>>>(S, src, count, d.counters, d_out);
         CU(cudaGetLastError());
-        CU(cudaEventRecord(d.ev[1], d.stream));
-        CU(cudaEventRecord(d.ev_mid, d.stream));
-        CU(cudaEventRecord(d.ev_cta, d.stream));
-        CU(cudaEventRecord(d.ev[2], d.stream));
-        CU(cudaEventRecord(d.ev[3], d.stream));
+        for (int k = 1; k < 5; ++k) CU(cudaEventRecord(E.k[k], d.stream));
         d.launches += 1;
         return PA_OK;
     }
@@ -328,7 +368,7 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
                      win_spread <= 3500 && (uint64_t)d.bbuf_rows >= 2ull * ((uint64_t)c.max_len + 1);
     int rc = ensure_deferred(d, (size_t)count);
     if (rc) return rc;
-    CU(cudaEventRecord(d.ev[0], d.stream));
+    CU(cudaEventRecord(E.k[0], d.stream));
     bool stage2 = false, stage_cta = false, stage_gen = false;
     PairSource src2 = src;
     const unsigned int *count2 = nullptr;
@@ -368,25 +408,25 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             CU(cudaGetLastError());
             d.launches += 1;
         }
-        d.chunk_duo = true;
+        E.duo = true;
         stage2 = !(amb ? c.all_fast : c.all_pure) || (c.max_len > l16 && !win);       // something may have been deferred
         src2.idx = d.deferred;
         count2 = d.n_deferred;
     } else if (fast) {
         stage2 = true;
     }
-    CU(cudaEventRecord(d.ev[1], d.stream));
+    CU(cudaEventRecord(E.k[1], d.stream));
     if (stage2) {
         pa_warp32_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(
             S, sc, src2, count, count2, d.counters + 1, d.bbuf, d.bbuf_rows, d_out, d.deferred2, d.n_deferred + 1,
             route_long ? d.deferred3 : nullptr, d.n_deferred + 2, LONG_LEN);
         CU(cudaGetLastError());
         d.launches += 1;
-        d.chunk_fast = true;
+        E.fast = true;
         stage_cta = route_long;
         stage_gen = !c.all_pure;
     }
-    CU(cudaEventRecord(d.ev_mid, d.stream));
+    CU(cudaEventRecord(E.k[2], d.stream));
     if (stage_cta) {
         PairSource src3 = src;
         src3.idx = d.deferred3;
@@ -394,16 +434,15 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             S, sc, src3, d.n_deferred + 2, d.counters + 3, d.bbuf, d.bbuf_rows, d_out);
         CU(cudaGetLastError());
         d.launches += 1;
-        d.chunk_cta = true;
+        E.cta = true;
     }
-    CU(cudaEventRecord(d.ev_cta, d.stream));
-    CU(cudaEventRecord(d.ev[2], d.stream));
+    CU(cudaEventRecord(E.k[3], d.stream));
     if (!fast) {
         pa_warp_dp_kernel<KGEN, true><<<d.grid_gen, threads, 0, d.stream>>>(
             S, sc, src, count, nullptr, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
         CU(cudaGetLastError());
         d.launches += 1;
-        d.chunk_gen = true;
+        E.gen = true;
     } else if (stage_gen) {
         PairSource src4 = src;
         src4.idx = d.deferred2;
@@ -411,29 +450,37 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
             S, sc, src4, count, d.n_deferred + 1, d.counters + 2, d.bbuf, d.bbuf_rows, d_out, nullptr, nullptr);
         CU(cudaGetLastError());
         d.launches += 1;
-        d.chunk_gen = true;
+        E.gen = true;
     }
-    CU(cudaEventRecord(d.ev[3], d.stream));
+    CU(cudaEventRecord(E.k[4], d.stream));
     return PA_OK;
 }
 
-int collect_chunk_times(Device &d) {
+// Kernel times of a finished chunk (its events are complete once `done` / k[4] has been waited for).
+int collect_chunk_times(Device &d, const Device::ChunkEvents &E, bool with_d2h) {
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
-    if (d.chunk_duo) d.duo_ms += ms;
-    CU(cudaEventElapsedTime(&ms, d.ev[1], d.ev_mid));
-    if (d.chunk_fast) d.fast_ms += ms;
-    CU(cudaEventElapsedTime(&ms, d.ev_mid, d.ev_cta));
-    if (d.chunk_cta) d.cta_ms += ms;
-    CU(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]));
-    if (d.chunk_gen) d.gen_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.k[0], E.k[1]));
+    if (E.duo) d.duo_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.k[1], E.k[2]));
+    if (E.fast) d.fast_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.k[2], E.k[3]));
+    if (E.cta) d.cta_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.k[3], E.k[4]));
+    if (E.gen) d.gen_ms += ms;
+    if (with_d2h) {
+        CU(cudaEventElapsedTime(&ms, E.k[4], E.done));
+        d.d2h_ms += ms;
+    }
     return PA_OK;
 }
 
 // Run one device's share [first, first+count) of the triangle (or of the
 // explicit lists) and deliver records to host memory `out` (out[0] is element
-// `first`).  Chunks are double-buffered: the kernel of chunk k+1 runs while
-// chunk k travels to the host and is copied into the caller's buffer.
+// `first`).  Two chunks are in flight: the kernels of chunk k+1 are enqueued
+// right behind those of chunk k on d.stream (no host synchronisation in
+// between), chunk k's records travel to pinned memory on copy_stream while
+// chunk k+1 computes, and the host copies chunk k-1 into the caller's buffer
+// meanwhile.  The host only ever waits for the chunk two launches back.
 int run_range(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_t count,
               const uint32_t *h_ia, const uint32_t *h_ib, pa_pair_result *out, pa_pair_result *d_resident) {
     CU(cudaSetDevice(d.id));
@@ -462,40 +509,36 @@ int run_range(Context &c, Device &d, const pa_params &p, uint64_t first, uint64_
     uint64_t done = 0;
     int slot = 0;
     struct Pending { bool active = false; uint64_t off = 0, n = 0; } pend[2];
+    // wait for the chunk in `s`, read its timings, hand its records to the caller
     auto drain = [&](int s) -> int {
         if (!pend[s].active) return PA_OK;
-        CU(cudaEventSynchronize(d.ev_done[s]));
-        memcpy(out + pend[s].off, d.h_stage[s], pend[s].n * sizeof(pa_pair_result));
+        Device::ChunkEvents &E = d.ce[s];
+        CU(cudaEventSynchronize(d_resident ? E.k[4] : E.done));
+        int r = collect_chunk_times(d, E, !d_resident);
+        if (r) return r;
+        if (!d_resident) memcpy(out + pend[s].off, d.h_stage[s], pend[s].n * sizeof(pa_pair_result));
         pend[s].active = false;
         return PA_OK;
     };
     while (done < count) {
         const uint64_t nthis = std::min<uint64_t>(chunk, count - done);
         pa_pair_result *dst = d_resident ? d_resident + done : d.d_out[slot];
-        if (!d_resident) { rc = drain(slot); if (rc) return rc; }
-        rc = launch_chunk(c, d, p, first + done, nthis, h_ia ? d.d_ia + done : nullptr, h_ia ? d.d_ib + done : nullptr, dst);
+        rc = drain(slot);            // the chunk two launches back: its events, d_out and h_stage are free again
+        if (rc) return rc;
+        Device::ChunkEvents &E = d.ce[slot];
+        rc = launch_chunk(c, d, p, first + done, nthis, h_ia ? d.d_ia + done : nullptr, h_ia ? d.d_ib + done : nullptr, dst, E);
         if (rc) return rc;
         if (!d_resident) {
-            // copy on the same stream (ordered after the kernels); the host memcpy of
-            // the previous chunk overlaps the next kernel
-            CU(cudaMemcpyAsync(d.h_stage[slot], dst, nthis * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
-            CU(cudaEventRecord(d.ev_done[slot], d.stream));
-            pend[slot].active = true; pend[slot].off = done; pend[slot].n = nthis;
+            CU(cudaStreamWaitEvent(d.copy_stream, E.k[4], 0));
+            CU(cudaMemcpyAsync(d.h_stage[slot], dst, nthis * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.copy_stream));
+            CU(cudaEventRecord(E.done, d.copy_stream));
         }
-        // kernel events of this chunk are reused by the next launch: wait for them
-        CU(cudaEventSynchronize(d.ev[3]));
-        rc = collect_chunk_times(d);
-        if (rc) return rc;
-        if (!d_resident) {
-            float ms = 0;
-            CU(cudaEventSynchronize(d.ev_done[slot]));
-            CU(cudaEventElapsedTime(&ms, d.ev[3], d.ev_done[slot]));
-            d.d2h_ms += ms;
-        }
+        pend[slot].active = true; pend[slot].off = done; pend[slot].n = nthis;
         done += nthis;
         slot ^= 1;
     }
-    if (!d_resident) { rc = drain(0); if (rc) return rc; rc = drain(1); if (rc) return rc; }
+    rc = drain(slot); if (rc) return rc;        // older chunk first
+    rc = drain(slot ^ 1); if (rc) return rc;
     CU(cudaStreamSynchronize(d.stream));
     return PA_OK;
 }
@@ -518,7 +561,7 @@ const char *pa_last_error(void) { return g_err.c_str(); }
 
 int pa_init(const int *devices, int n_dev) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx) { for (auto &d : g_ctx->dev) free_device(d); delete g_ctx; g_ctx = nullptr; }
+    if (g_ctx) { for (auto &d : g_ctx->dev) free_device(d); if (g_ctx->host_masks) cudaFreeHost(g_ctx->host_masks); delete g_ctx; g_ctx = nullptr; }
     int avail = 0;
     cudaError_t e = cudaGetDeviceCount(&avail);
     if (e != cudaSuccess || avail <= 0)
@@ -555,9 +598,10 @@ int pa_init(const int *devices, int n_dev) {
         cudaError_t e2 = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
         for (auto &ev : d.ev) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
-        for (auto &ev : d.ev_done) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
-        if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_mid);
-        if (e2 == cudaSuccess) e2 = cudaEventCreate(&d.ev_cta);
+        for (auto &ce : d.ce) {
+            for (auto &ev : ce.k) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
+            if (e2 == cudaSuccess) e2 = cudaEventCreate(&ce.done);
+        }
         if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 5 * sizeof(unsigned long long));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
         int occ = 0;
@@ -608,6 +652,7 @@ void pa_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx) return;
     for (auto &d : g_ctx->dev) free_device(d);
+    if (g_ctx->host_masks) cudaFreeHost(g_ctx->host_masks);
     delete g_ctx;
     g_ctx = nullptr;
 }
@@ -663,12 +708,8 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     if (!offsets || (!masks && n_seq && offsets[n_seq] > 0)) return fail(PA_EINVAL, "NULL sequence buffer");
     Context &c = *g_ctx;
     std::vector<uint32_t> len(n_seq), off2(n_seq), off4(n_seq);
-    std::vector<uint8_t> pure(n_seq), fastok(n_seq);
-    std::vector<uint32_t> exc, exc_off((size_t)n_seq + 1, 0);
-    bool all_fast = true;
     uint64_t w2 = 0, w4 = 0;
     uint32_t max_len = 0;
-    bool all_pure = true;
     for (uint32_t s = 0; s < n_seq; ++s) {
         if (offsets[s + 1] < offsets[s]) return fail(PA_EINVAL, "offsets not ascending at %u", s);
         const uint64_t L = offsets[s + 1] - offsets[s];
@@ -680,33 +721,94 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         w4 += ((L + 7) / 8 + 3) / 4 * 4;
         if (w4 > 0xffffffffull) return fail(PA_ERANGE, "sequence set too large");
     }
-    std::vector<uint32_t> p2(std::max<uint64_t>(w2, 4), 0), p4(std::max<uint64_t>(w4, 4), 0);
-    for (uint32_t s = 0; s < n_seq; ++s) {
-        const uint8_t *src = masks + offsets[s];
-        bool pr = true;
-        for (uint32_t k = 0; k < len[s]; ++k) {
-            const uint32_t v = src[k] & 15u;
-            p4[off4[s] + (k >> 3)] |= v << ((k & 7) * 4);
-            uint32_t code = 0;
-            switch (v) { case 1: code = 0; break; case 2: code = 1; break; case 4: code = 2; break; case 8: code = 3; break; default: pr = false; }
-            p2[off2[s] + (k >> 4)] |= code << ((k & 15) * 2);
+    const uint64_t n_bases = n_seq ? offsets[n_seq] - offsets[0] : 0;
+    const uint64_t base0 = n_seq ? offsets[0] : 0;
+    // The host keeps the sets (pa_align_pair_traceback rebuilds strings from them) in pinned memory, which is also
+    // where the devices fetch them from.  Packing is the devices' job (pa_pack_kernel): the host only scans.
+    if (n_bases > c.host_masks_cap) {
+        if (c.host_masks) cudaFreeHost(c.host_masks);
+        c.host_masks = nullptr; c.host_masks_cap = 0;
+        CU(cudaMallocHost(&c.host_masks, (size_t)std::max<uint64_t>(n_bases, 4096)));
+        c.host_masks_cap = std::max<uint64_t>(n_bases, 4096);
+    }
+    if (n_bases) memcpy(c.host_masks, masks + base0, (size_t)n_bases);
+    c.host_offsets.resize((size_t)n_seq + 1);
+    for (uint32_t s = 0; s <= n_seq; ++s) c.host_offsets[s] = offsets[s] - base0;
+    c.row_items.assign((size_t)n_seq + 1, 0);
+    for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
+
+    auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
+        // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
+        if (bytes <= cap && *ptr) return cudaSuccess;
+        cudaFree(*ptr);
+        *ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(ptr, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    };
+    const size_t nidx = std::max<size_t>(n_seq, 1);
+    const size_t words2 = (size_t)std::max<uint64_t>(w2, 4), words4 = (size_t)std::max<uint64_t>(w4, 4);
+    for (auto &d : c.dev) {         // raw sets + geometry to every device, packing there; all asynchronous
+        CU(cudaSetDevice(d.id));
+        CU(grow((void **)&d.row_items, d.cap_row_items, c.row_items.size() * sizeof(unsigned long long)));
+        CU(grow((void **)&d.p2, d.cap_p2, words2 * 4));
+        CU(grow((void **)&d.p4, d.cap_p4, words4 * 4));
+        CU(grow((void **)&d.off2, d.cap_off2, nidx * 4));
+        CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
+        CU(grow((void **)&d.len, d.cap_len, nidx * 4));
+        CU(grow((void **)&d.pure, d.cap_pure, nidx));
+        CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
+        CU(grow((void **)&d.exc_off, d.cap_exc_off, (nidx + 1) * 4));
+        CU(grow((void **)&d.raw, d.cap_raw, (size_t)std::max<uint64_t>(n_bases, 16)));
+        CU(grow((void **)&d.raw_off, d.cap_raw_off, (nidx + 1) * sizeof(unsigned long long)));
+        d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
+        if (max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
+        CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
+        CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        if (n_seq) {
+            if (n_bases) CU(cudaMemcpyAsync(d.raw, c.host_masks, (size_t)n_bases, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.raw_off, c.host_offsets.data(), ((size_t)n_seq + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            pa_pack_kernel<<<(unsigned)std::min<uint32_t>(n_seq, 65535u * 16u), 128, 0, d.stream>>>(
+                d.raw, d.raw_off, d.len, d.off2, d.off4, n_seq, d.p2, d.p4, d.pure);
+            CU(cudaGetLastError());
+        } else {
+            CU(cudaMemsetAsync(d.p2, 0, 16, d.stream));
+            CU(cudaMemsetAsync(d.p4, 0, 16, d.stream));
         }
+    }
+
+    // Meanwhile on the host: which sequences are plain A/C/G/T (a branch-free scan the compiler vectorises), and for
+    // the others the sparse-ambiguity description of the s16x2 AMB variant: no gap character, positions 1..15 plain,
+    // ranges of DIFFERENT sets at least 16 plain bases apart, at most EXC_MAX ranges (a range = up to 255 equal sets).
+    std::vector<uint8_t> pure(n_seq), fastok(n_seq);
+    std::vector<uint32_t> exc, exc_off((size_t)n_seq + 1, 0);
+    bool all_fast = true, all_pure = true, any_sparse = false;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        const uint8_t *src = c.host_masks + c.host_offsets[s];
+        const uint32_t L = len[s];
+        uint8_t bad = 0;
+        for (uint32_t k = 0; k < L; ++k) {
+            const uint8_t v = src[k] & 15u;
+            bad |= (uint8_t)((v & (uint8_t)(v - 1u)) | (uint8_t)(v == 0));     // not exactly one bit set
+        }
+        const bool pr = bad == 0;
         pure[s] = pr ? 1 : 0;
         all_pure = all_pure && pr;
-        // Sparse ambiguity codes (s16x2 AMB variant): no gap character, positions 1..15 plain, ranges of DIFFERENT sets at
-        // least 16 plain bases apart, at most EXC_MAX ranges (a range = up to 255 equal sets in a row)
         exc_off[s] = (uint32_t)exc.size();
         bool ok = true;
         if (!pr) {
             const size_t first_range = exc.size();
             int last_end = -1000;           // end (exclusive) of the previous range
             uint32_t last_set = 0;
-            for (uint32_t k = 0; k < len[s] && ok; ) {
+            for (uint32_t k = 0; k < L && ok; ) {
                 const uint32_t v = src[k] & 15u;
                 if (v == 0) { ok = false; break; }
                 if (v == 1 || v == 2 || v == 4 || v == 8) { ++k; continue; }
                 uint32_t run = 1;
-                while (k + run < len[s] && (src[k + run] & 15u) == v && run < 255) ++run;
+                while (k + run < L && (src[k + run] & 15u) == v && run < 255) ++run;
                 if (k >= 1 && k <= 15) ok = false;
                 if (k == 0 && run > 1) ok = false;
                 if (last_set != v && (int)k - last_end < 16) ok = false;
@@ -716,21 +818,19 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
             }
             if (exc.size() - first_range > (size_t)EXC_MAX) ok = false;
             if (!ok) exc.resize(first_range);
+            any_sparse = any_sparse || ok;
         }
         fastok[s] = ok ? 1 : 0;
         all_fast = all_fast && ok;
     }
     exc_off[n_seq] = (uint32_t)exc.size();
     c.n_seq = n_seq;
-    c.host_masks.assign(masks, masks + offsets[n_seq]);
-    c.host_offsets.assign(offsets, offsets + n_seq + 1);
     c.host_pure = pure;
     c.len = len;
     c.max_len = max_len;
     c.all_pure = all_pure;
     c.all_fast = all_fast;
-    c.any_sparse = false;
-    for (uint32_t s = 0; s < n_seq; ++s) c.any_sparse = c.any_sparse || (fastok[s] && !pure[s]);
+    c.any_sparse = any_sparse;
     c.tri.build(len.data(), n_seq);
     // strip width of the s16x2 kernel: chosen per work item inside the kernel (0); PAIRALIGN_KDUO=8|12 forces one width
     c.kduo = (c.kduo_forced == 8 || c.kduo_forced == 12) ? c.kduo_forced : 0;
@@ -739,42 +839,11 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
         c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
     }
-    c.row_items.assign((size_t)n_seq + 1, 0);
-    for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
-
     for (auto &d : c.dev) {
         CU(cudaSetDevice(d.id));
-        // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
-        auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
-            if (bytes <= cap && *ptr) return cudaSuccess;
-            cudaFree(*ptr);
-            *ptr = nullptr; cap = 0;
-            cudaError_t e = cudaMalloc(ptr, bytes);
-            if (e == cudaSuccess) cap = bytes;
-            return e;
-        };
-        const size_t nidx = std::max<size_t>(n_seq, 1);
-        CU(grow((void **)&d.row_items, d.cap_row_items, c.row_items.size() * sizeof(unsigned long long)));
-        CU(grow((void **)&d.p2, d.cap_p2, p2.size() * 4));
-        CU(grow((void **)&d.p4, d.cap_p4, p4.size() * 4));
-        CU(grow((void **)&d.off2, d.cap_off2, nidx * 4));
-        CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
-        CU(grow((void **)&d.len, d.cap_len, nidx * 4));
-        CU(grow((void **)&d.pure, d.cap_pure, nidx));
-        CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
         CU(grow((void **)&d.exc, d.cap_exc, std::max<size_t>(exc.size(), 1) * 4));
-        CU(grow((void **)&d.exc_off, d.cap_exc_off, (nidx + 1) * 4));
-        d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
-        if (max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
-        CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
-        CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
-        CU(cudaMemcpyAsync(d.p2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice, d.stream));
-        CU(cudaMemcpyAsync(d.p4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice, d.stream));
         if (n_seq) {
-            CU(cudaMemcpyAsync(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.pure, pure.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
+            // d.pure was written by pa_pack_kernel from the same bytes; the host's copy is what launch decisions use
             CU(cudaMemcpyAsync(d.fastok, fastok.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
             CU(cudaMemcpyAsync(d.exc_off, exc_off.data(), ((size_t)n_seq + 1) * 4, cudaMemcpyHostToDevice, d.stream));
             if (!exc.empty()) CU(cudaMemcpyAsync(d.exc, exc.data(), exc.size() * 4, cudaMemcpyHostToDevice, d.stream));
@@ -1052,9 +1121,9 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
     return PA_OK;
 }
 
-int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
-                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
-    std::lock_guard<std::mutex> lk(g_mu);
+// pa_align_pairs_ops with g_mu already held by the caller
+static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
+                    uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
     if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
     int rc = check_params(params);
     if (rc) return rc;
@@ -1121,25 +1190,28 @@ int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32
     return PA_OK;
 }
 
+int pa_align_pairs_ops(const pa_params *params, const uint32_t *ia, const uint32_t *ib, uint64_t count,
+                       uint8_t *ops, uint64_t ops_cap, uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return ops_impl(params, ia, ib, count, ops, ops_cap, op_offsets, n_ops, res);
+}
+
 int pa_align_pair_traceback(const pa_params *params, uint32_t a, uint32_t b, uint8_t *ax, uint8_t *ay, uint32_t cap,
                             uint32_t *alen, pa_pair_result *res) {
-    uint32_t n = 0, m = 0;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
-        if (a >= g_ctx->n_seq || b >= g_ctx->n_seq) return fail(PA_ERANGE, "sequence index out of range");
-        if (!ax || !ay || !alen) return fail(PA_EINVAL, "NULL output buffer");
-        n = g_ctx->len[a]; m = g_ctx->len[b];
-        if (cap < n + m) return fail(PA_EINVAL, "alignment buffers need n+m = %u bytes", n + m);
-        if (n == 0 || m == 0) return fail(PA_EINVAL, "empty sequence: the reference's behaviour is undefined here");
-    }
+    // one lock from the length check to the rendering: a concurrent pa_upload_sequences cannot swap the set in between
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    if (a >= g_ctx->n_seq || b >= g_ctx->n_seq) return fail(PA_ERANGE, "sequence index out of range");
+    if (!ax || !ay || !alen) return fail(PA_EINVAL, "NULL output buffer");
+    const uint32_t n = g_ctx->len[a], m = g_ctx->len[b];
+    if (cap < n + m) return fail(PA_EINVAL, "alignment buffers need n+m = %u bytes", n + m);
+    if (n == 0 || m == 0) return fail(PA_EINVAL, "empty sequence: the reference's behaviour is undefined here");
     std::vector<uint8_t> ops((size_t)n + m);
     uint64_t off[2];
     uint32_t nops = 0;
-    int rc = pa_align_pairs_ops(params, &a, &b, 1, ops.data(), ops.size(), off, &nops, res);
+    int rc = ops_impl(params, &a, &b, 1, ops.data(), ops.size(), off, &nops, res);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    const uint8_t *x = g_ctx->host_masks.data() + g_ctx->host_offsets[a], *y = g_ctx->host_masks.data() + g_ctx->host_offsets[b];
+    const uint8_t *x = g_ctx->host_masks + g_ctx->host_offsets[a], *y = g_ctx->host_masks + g_ctx->host_offsets[b];
     uint32_t i = 0, j = 0;
     for (uint32_t k = 0; k < nops; ++k) {
         ax[k] = ops[k] == 2 ? 0 : x[i++];

@@ -15,6 +15,12 @@
 //     clustering "comp value" (src/indexedfasta.cpp:66-73, src/indexedfasta.h:34);
 //   * text before the first header belongs to an accession "" (a side effect
 //     of `++index[accno].N` with an empty accno, src/indexedfasta.cpp:70).
+// One deliberate deviation: input WITHOUT a final newline.  The reference's
+// `cin >> noskipws` loop then duplicates the last character (stdin: the last
+// sequence gains a base), and from a file its stream is left failed after the
+// first read of the last record, so every later read returns an empty sequence.
+// Here such input reads like the same text with the newline
+// (tests/test_host_fuzz_vs_reference.py::test_input_without_final_newline...).
 #pragma once
 #include <istream>
 #include <map>

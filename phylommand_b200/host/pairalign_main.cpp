@@ -55,7 +55,6 @@ struct Options {
     int min_length = 100;
     bool only_lead = false;
     std::string format = "fasta";
-    int n_threads = 1;
 };
 
 // argv_parser::pars_sub_args (src/argv_parser.cpp:53-72): split on `sep`, backslash escapes
@@ -74,7 +73,7 @@ std::vector<std::string> split_sub_args(const char *arg, char sep) {
 }
 
 void print_help() {
-    // src/pairalign.cpp:312-403 (default build: no DATABASE; -T is accepted but batches replace threads)
+    // src/pairalign.cpp:312-403 (default build: no DATABASE, no PTHREAD, so -T / --threads is 'not recognized' here as it is there)
     std::cout << "Pairalign " << kVersion << " will perform pairwise alignment of DNA sequences given in fasta\n"
               << "format through standard in.\n"
               << "(c) Martin Ryberg " << kYear << ".\n\n"
@@ -433,7 +432,8 @@ void pipeline(uint64_t total, uint64_t chunk, Produce produce, Consume consume) 
         const uint64_t next = first + chunk;
         std::thread worker;
         if (next < total) worker = std::thread(fill, slot ^ 1, next);
-        consume(first, buf[slot]);
+        // a throwing consumer must not leave the worker joinable (its destructor would call std::terminate)
+        try { consume(first, buf[slot]); } catch (...) { if (worker.joinable()) worker.join(); throw; }
         if (worker.joinable()) worker.join();
         slot ^= 1;
     }
@@ -606,12 +606,18 @@ void run_pairfasta(const Options &opt, Out &out) {
     std::istream *input = &std::cin;
     if (!opt.file_name.empty()) { file.open(opt.file_name.c_str()); input = &file; }
     if (!opt.quiet) std::cerr << "Opened pairfa database." << std::endl;
-    std::map<std::string, std::string> taxon_strings;
-    if (!opt.taxonomy_file.empty()) read_taxonomy(opt.taxonomy_file, taxon_strings);
-    else taxon_strings["default"] = "all";                     // src/pairalign.cpp:440-445
     const char mode = opt.output_mode;
+    std::map<std::string, std::string> taxon_strings;
+    if (!opt.taxonomy_file.empty()) {                          // src/pairalign.cpp:409-439
+        if (!opt.quiet) std::cerr << "Parsing taxonomy from " << opt.taxonomy_file << "." << std::endl;
+        if (read_taxonomy(opt.taxonomy_file, taxon_strings) && !opt.quiet) std::cerr << "Added taxonomy." << std::endl;
+    } else {
+        taxon_strings["default"] = "all";                      // src/pairalign.cpp:440-445
+        if (!opt.quiet && (mode == 'A' || mode == 'B')) std::cerr << "All sequences will be treated as from same taxon." << std::endl;
+    }
     std::ofstream groups_file;
     if (mode == 'A' || mode == 'B') {
+        if (!opt.quiet) std::cerr << "No alignment_groups file/table present. Trying to create it." << std::endl;
         const std::string name = opt.file_name.empty() ? "sequence.alignment_groups" : opt.file_name + ".alignment_groups";
         groups_file.open(name.c_str());
         if (!groups_file.is_open()) { std::cerr << "Failed to create alignment_groups." << std::endl; return; }
@@ -625,7 +631,9 @@ void run_pairfasta(const Options &opt, Out &out) {
                       << ". Will only define alignment groups and not cluster." << std::endl;
             return;
         }
+        if (!opt.quiet) std::cerr << "Using the cut off: " << cut_off << "." << std::endl;
     }
+    if (!opt.quiet) std::cerr << "Checking " << table << std::endl;
     // read every pair with the reference's character state machine; taxon strings found in the
     // headers are APPENDED to the map each time an accession is seen (src/seqdatabase.cpp:55-56)
     std::vector<PairRecord> pairs;
@@ -661,6 +669,7 @@ void run_pairfasta(const Options &opt, Out &out) {
         if (last) break;
     }
     if (!opt.quiet) std::cerr << "Starting pairwise alignment." << std::endl;
+    if (!ok) std::cerr << "Could not initiate sequence retrieval. No aligning done for " << table << "." << std::endl;   // src/pairalign.cpp:632
     SeqpairBatch batch;
     Replayer rp(opt, cut_off, batch, out);
     // accession dictionary in ascending order = the reference's map order for printed clusters
@@ -674,7 +683,7 @@ void run_pairfasta(const Options &opt, Out &out) {
         ia.push_back((uint32_t)batch.add_sequence(r.seq1));
         ib.push_back((uint32_t)batch.add_sequence(r.seq2));
     }
-    if (opt.matrix && mode == 'd')
+    if (ok && opt.matrix && mode == 'd')
         out.put("Proportion different/Similarity/Jukes-Cantor distance/Difference between JC and similarity\n");
     pa_params params{7, -5, -15, -1, opt.aligned ? 1 : 0};
     std::vector<pa_pair_result> recs(pairs.size());
@@ -705,6 +714,8 @@ void run_pairfasta(const Options &opt, Out &out) {
     if (opt.matrix && !pairs.empty() && !last_accno2.empty()) { out.put('\n'); out.put(last_accno2); out.put('\n'); }
     if (!opt.quiet) std::cerr << std::endl;
     if (mode == 'A' || mode == 'B') {
+        if (!opt.quiet)
+            std::cerr << "Finished aligning. Calculating mad to determine taxonomic level suitable for alignment." << std::endl;
         const std::string levels = rp.deviations.get_levels();
         out.put("# Alignment groups for "); out.put(table); out.put('\n');
         out.put("#    Alignment groups: "); out.put(levels); out.put('\n');
@@ -737,11 +748,6 @@ int main(int argc, char *argv[]) {
         else if (is("-n", "--names")) opt.output_names = true;
         else if (is("-A", "--aligned")) opt.aligned = true;
         else if (is("-v", "--verbose")) opt.quiet = false;
-        else if (is("-T", "--threads")) {
-            ++i;
-            if (i < argc && argv[i][0] != '-') opt.n_threads = atoi(argv[i]);
-            else { std::cerr << "--threads or -T must be followed by a integer value, e.g. -T 4. Quiting quietly." << std::endl; return 0; }
-        }
         else if (is("-f", "--file")) {
             if (i + 1 < argc && argv[i + 1][0] != '-') opt.file_name = argv[++i];
             else { std::cerr << "-f/--file needs to be followed by a file name." << std::endl; return 1; }
@@ -807,10 +813,6 @@ int main(int argc, char *argv[]) {
     bool error_flag = false;
     if (opt.min_length < 0) {
         std::cerr << "Minimum sequence length to consider for clustering must be positive integer, e.g. 100." << std::endl;
-        error_flag = true;
-    }
-    if (opt.n_threads < 1) {
-        std::cerr << "Number of threads (--threads or -T) must be 1 or more (not " << opt.n_threads << "), e.g. 4." << std::endl;
         error_flag = true;
     }
     if (error_flag) { std::cerr << "Quitting quietly." << std::endl; return 0; }

@@ -1,12 +1,14 @@
-"""Extended GPU checks written at the end of round 1, after the last GPU session: they have NOT run on a GPU yet and
-are therefore switched off unless PAIRALIGN_EXTENDED=1 (enable them in the first GPU session of the next round, fix
-what they find, then drop the switch).
+"""GPU checks at the sizes and on the inputs where parity is hardest (all ran green on a B200 in round 2, first session):
 
   * the differential fuzz of tests/test_host_fuzz_vs_reference.py through the real command line (CUDA module)
     against the reference binary that travels in oracle/_ref/;
   * CUDA vs oracle on inputs where ties decide everything (repeats, containment, overlapping ends, all-ambiguous);
-  * the op strings of two 30 kb pairs against the oracle's 2-bit-move walk (exact parity of -a at config 5 size)."""
+  * the op strings of two 30 kb pairs against the oracle's 2-bit-move walk (exact parity of -a at config 5 size);
+  * one 30 kb x 30 kb and one 30 kb x 400 bp pair, statistics records against the oracle's forward form;
+  * the command line against the reference's own output on the first 64 sequences of config 3 and the first 128 of
+    config 4 (tests/golden/prefix/, made by oracle/make_prefix_golden.py), SURVEY.md section 8(d)'s prefix rule."""
 import os
+import shutil
 import subprocess
 from pathlib import Path
 
@@ -15,8 +17,7 @@ import pytest
 
 from phylommand_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PAIRALIGN_EXTENDED") != "1", reason="not yet validated on a GPU (PAIRALIGN_EXTENDED=1 runs them)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = Path(__file__).resolve().parent.parent
 REF = ROOT / "oracle" / "_ref" / "pairalign"
@@ -92,3 +93,39 @@ def test_alignments_of_30kb_pairs_equal_the_oracle(gpu, oracle):
         assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
         got = ops[int(off[k]):int(off[k]) + int(n_ops[k])]
         assert got.tobytes() == want.tobytes(), (ia[k], ib[k])
+
+
+def test_30kb_pairs_statistics_equal_the_oracle(gpu, oracle):
+    """BASELINE.json config 5 size against the oracle (O(n + m) memory forward form): a 30 kb x 30 kb pair and a
+    30 kb x 400 bp pair, in both orientations, on every route a long pair can take -- the floating-window s16x2
+    kernel (triangle range), the int32 warp kernel / CTA-per-pair kernel (explicit list)."""
+    _, seqs = synth.make_long(2, 1005, length=30000, spread=0.05)
+    _, short = synth.make_random(1, 1007, 400, 400)
+    enc = [synth.to_masks(s) for s in seqs + short]
+    gpu.upload(enc)
+    from concurrent.futures import ThreadPoolExecutor
+    keys = ((0, 1), (0, 2), (1, 2), (1, 0), (2, 0))
+    with ThreadPoolExecutor(len(keys)) as ex:       # the oracle is plain C behind ctypes: the calls run side by side
+        want = dict(zip(keys, ex.map(lambda ab: tuple(oracle.align_forward(enc[ab[0]], enc[ab[1]])), keys)))
+    got = gpu.align_all_pairs()
+    assert [tuple(r) for r in got] == [want[(0, 1)], want[(0, 2)], want[(1, 2)]]
+    ia, ib = np.array([0, 1, 2, 0]), np.array([1, 0, 0, 2])
+    lst = gpu.align_pairs(ia, ib)
+    assert [tuple(r) for r in lst] == [want[(0, 1)], want[(1, 0)], want[(2, 0)], want[(0, 2)]]
+
+
+PREFIX = ROOT / "tests" / "golden" / "prefix"
+
+
+@pytest.mark.parametrize("tag,flags,groups", [("c3_64", ["-j", "-n", "-m"], False),
+                                              ("c4_128", ["--group", "both:cut-off=0.97"], True)])
+def test_command_line_on_config_prefixes_matches_the_reference(cli, tmp_path, tag, flags, groups):
+    """First 64 sequences of config 3 / first 128 of config 4 (with taxon strings): stdout and the .alignment_groups
+    file byte for byte what the unmodified reference printed (about 10 CPU-minutes each there)."""
+    shutil.copy(PREFIX / f"{tag}.fst", tmp_path / f"{tag}.fst")
+    r = subprocess.run([str(cli), *flags, f"{tag}.fst"], cwd=tmp_path, capture_output=True, timeout=600,
+                       env=dict(os.environ, PAIRALIGN_DEVICES="0"))
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-1000:]
+    assert r.stdout == (PREFIX / f"{tag}.out").read_bytes()
+    if groups:
+        assert (tmp_path / f"{tag}.fst.alignment_groups").read_bytes() == (PREFIX / f"{tag}.alignment_groups").read_bytes()

@@ -281,14 +281,14 @@ LONG_AND_ERRORS = [["--jc_distance", "--names", "--matrix"], ["--distances", "--
                    ["--similarity"], ["--difference", "--names", "--matrix"], ["--alignments", "--names"], ["--aligned", "--jc_distance"],
                    ["--group", "both:cut-off=0.9"], ["--group", "alignment_groups", "--verbose"], ["-j", "-n", "-m", "-v"],
                    ["--format", "fasta", "-j"], ["--format", "pairfa", "-j"], ["-h"], ["--help"], ["-j", "-x"], ["--format", "xml"],
-                   ["-g", "nonsense"], ["-g", "both:foo=1"], ["-g"]]
+                   ["-g", "nonsense"], ["-g", "both:foo=1"], ["-g"], ["-T", "2", "-j", "-m"], ["-T"], ["--threads", "0"]]
 
 
 @pytest.mark.parametrize("seed", range(6))
 def test_long_options_stdin_and_argument_errors_against_the_reference(exe, tmp_path, seed):  # noqa: F811
     """Long option names, input on stdin (the alignment groups then go to sequence.alignment_groups), help, and
-    the argument errors with their exit codes.  (-T/--threads is left out on purpose: only the reference's PTHREAD
-    build knows it; here it is accepted and ignored.)"""
+    the argument errors with their exit codes.  -T/--threads is 'not recognized' by the reference's default build (no
+    PTHREAD) and therefore here."""
     text = make_case(5000 + seed, group=(seed % 2 == 0))
     for flags in LONG_AND_ERRORS:
         for use_stdin in (False, True):
@@ -329,3 +329,59 @@ def test_verbose_stderr_against_the_reference(exe, tmp_path, seed):  # noqa: F81
             r = subprocess.run([str(binary), *flags, "-v", "in.fst"], cwd=d, capture_output=True, timeout=120)
             outs.append((r.returncode, r.stdout, norm(r.stderr, binary)))
         assert outs[0] == outs[1], (flags, seed)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_verbose_stderr_in_pairfst_mode_against_the_reference(exe, tmp_path, seed):  # noqa: F811
+    """--format pairfst with -v: the same messages as the reference on stderr ('All sequences will be treated as from
+    same taxon.', 'No alignment_groups file/table present...', 'Using the cut off', 'Checking <table>', 'Finished
+    aligning...'), with and without a taxonomy file; and the un-silenced 'Could not initiate sequence retrieval' line
+    for a pairfst file that cannot be read."""
+    import re
+
+    def norm(raw, path):
+        text = raw.decode(errors="replace").replace(str(path), "BIN")
+        return re.sub(r"(Sat|Sun|Mon|Tue|Wed|Thu|Fri) \w{3} +\d+ [\d:]+ \d{4}", "DATE", text)
+
+    (tmp_path / "in.fst").write_bytes(make_case(8000 + seed, group=False).encode())
+    ref, ours = run_both(exe, tmp_path, ["-a", "-n"], "in.fst")
+    assert ours[1] == ref[1]
+    names = sorted({ln[1:].split(b"|")[0].strip().decode() for ln in ref[1].split(b"\n") if ln.startswith(b">")})
+    tax = "Life; A|" + ",".join(names[: len(names) // 2]) + "\nLife; B|" + " ".join(names[len(names) // 2:]) + "\n"
+    cases = [(["--format", "pairfst", "-j", "-n"], "pairs.pairfst"), (["--format", "pairfst", "-g", "alignment_groups"], "pairs.pairfst"),
+             (["--format", "pairfst", "-g", "both:cut-off=0.9"], "pairs.pairfst"),
+             (["--format", "pairfst", "-g", "both:cut-off=0.9:taxonomy=tax.txt"], "pairs.pairfst"),
+             (["--format", "pairfst", "-g", "cluster:cut-off=0.95"], "pairs.pairfst"),
+             (["--format", "pairfst", "-d", "-m"], "missing.pairfst"), (["--format", "pairfst", "-g", "both"], "missing.pairfst")]
+    for flags, name in cases:
+        for verbose in (["-v"], []):
+            outs = []
+            for binary, sub in ((REF, "ref"), (exe, "ours")):
+                d = tmp_path / f"{sub}_v"
+                d.mkdir(exist_ok=True)
+                for old in d.iterdir():
+                    old.unlink()
+                (d / "pairs.pairfst").write_bytes(ref[1])
+                (d / "tax.txt").write_text(tax)
+                r = subprocess.run([str(binary), *flags, *verbose, name], cwd=d, capture_output=True, timeout=120)
+                made = sorted((p.name, p.read_bytes()) for p in d.iterdir() if p.name not in ("pairs.pairfst", "tax.txt"))
+                outs.append((r.returncode, r.stdout, norm(r.stderr, binary), made))
+            assert outs[0] == outs[1], (flags, name, verbose, seed)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_input_without_final_newline_reads_like_the_same_file_with_one(exe, tmp_path, seed):  # noqa: F811
+    """The one deliberate deviation of the FASTA front end (host/fasta_index.h): without a final newline
+    the reference duplicates the last character (stdin) or leaves its stream failed and reads empty sequences from
+    then on (file).  Here such input gives what the reference gives for the same text WITH the newline."""
+    text = make_case(9000 + seed, group=False)
+    assert text.endswith("\n")
+    for flags in (["-j", "-n", "-m"], ["-a", "-n"], ["-d"]):
+        (tmp_path / "in.fst").write_bytes(text.encode())
+        ref, _ = run_both(exe, tmp_path, flags, "in.fst")
+        d = tmp_path / "cut"
+        d.mkdir(exist_ok=True)
+        (d / "in.fst").write_bytes(text.rstrip("\r\n").encode())
+        from_file = subprocess.run([str(exe), *flags, "in.fst"], cwd=d, capture_output=True, timeout=120)
+        from_stdin = subprocess.run([str(exe), *flags], cwd=d, input=text.rstrip("\r\n").encode(), capture_output=True, timeout=120)
+        assert from_file.stdout == ref[1] and from_stdin.stdout == ref[1], (flags, seed)
