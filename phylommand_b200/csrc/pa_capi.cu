@@ -3,6 +3,7 @@
 // compute entry point needs a CUDA device.
 #include "pa_dp.cuh"
 #include "pa_dp32.cuh"
+#include "pa_dp_sets.cuh"
 #include "pa_peak.cuh"
 
 #include <algorithm>
@@ -69,7 +70,7 @@ struct Device {
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_duo_amb = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_duo_amb = 0, grid_sets = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -357,8 +358,9 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     // pairs too long for plain 16-bit scores stay on the s16x2 kernel (floating-window variant) unless they go to the
     // CTA kernel; the edge rows then take two bbuf entries each
     // (a gap extension beyond -1024 could wrap a 16-bit half before the maximum with the opening term is taken)
-    // sequences with sparse IUPAC codes: a second launch of the s16x2 kernel in its AMB form takes their items
-    const bool amb = duo && c.kduo == 0 && c.any_sparse && !c.no_amb;
+    // sequences with IUPAC ambiguity codes (no gap character): a second launch, the 4-bit-set form of the s16x2 kernel
+    // (pa_dp_sets.cuh), takes their items; it adds (match - mismatch) where two sets intersect, so that must be >= 0
+    const bool amb = duo && c.kduo == 0 && c.any_sparse && !c.no_amb && p.match >= p.mismatch;
     // ... and the values a lane holds at one time (13 columns, two rows, what its neighbour hands over) must fit the
     // window around its right edge with the storage bias in place: about 4000 either side of the re-base band
     // (stored values stay in [-32768 + |ge|, -16]); neighbouring states differ by at most one of each penalty
@@ -396,15 +398,13 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
                 d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
-        if (amb) {   // the items with sparse ambiguity codes: same work items, AMB variant (its own work counter)
+        if (amb) {   // the items with an ambiguous sequence: same work items, 4-bit-set variant (its own work counter)
             if (p.gap_ext == -1)
-                pa_warp_duo_kernel<-1, 1, -1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
-                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
-                    d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
+                pa_warp_sets_kernel<-1><<<d.grid_sets, threads, 0, d.stream>>>(
+                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
             else
-                pa_warp_duo_kernel<-1><<<d.grid_duo_amb, threads, 0, d.stream>>>(
-                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out,
-                    d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, 1);
+                pa_warp_sets_kernel<0><<<d.grid_sets, threads, 0, d.stream>>>(
+                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
             CU(cudaGetLastError());
             d.launches += 1;
         }
@@ -619,6 +619,9 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<-1>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<-1, 1, -1>, WARPS_PER_CTA * 32, 0);
         d.grid_duo_amb = std::max(1, std::min(occ, occ_c)) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1>, WARPS_PER_CTA * 32, 0);
+        d.grid_sets = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
@@ -627,7 +630,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_amb), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_amb), d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -780,9 +783,8 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         }
     }
 
-    // Meanwhile on the host: which sequences are plain A/C/G/T (a branch-free scan the compiler vectorises), and for
-    // the others the sparse-ambiguity description of the s16x2 AMB variant: no gap character, positions 1..15 plain,
-    // ranges of DIFFERENT sets at least 16 plain bases apart, at most EXC_MAX ranges (a range = up to 255 equal sets).
+    // Meanwhile on the host: which sequences are plain A/C/G/T and which of the others are free of gap characters
+    // (branch-free scans the compiler vectorises).
     std::vector<uint8_t> pure(n_seq), fastok(n_seq);
     std::vector<uint32_t> exc, exc_off((size_t)n_seq + 1, 0);
     bool all_fast = true, all_pure = true, any_sparse = false;
@@ -797,27 +799,14 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         const bool pr = bad == 0;
         pure[s] = pr ? 1 : 0;
         all_pure = all_pure && pr;
-        exc_off[s] = (uint32_t)exc.size();
+        exc_off[s] = 0;
+        // an ambiguous sequence stays on the s16x2 path (4-bit-set variant) unless it holds a gap character: '-' scores
+        // INT_MIN with 32-bit wrap-around in the reference (src/seqpair.cpp:192-193), which only the int32 kernel reproduces
         bool ok = true;
         if (!pr) {
-            const size_t first_range = exc.size();
-            int last_end = -1000;           // end (exclusive) of the previous range
-            uint32_t last_set = 0;
-            for (uint32_t k = 0; k < L && ok; ) {
-                const uint32_t v = src[k] & 15u;
-                if (v == 0) { ok = false; break; }
-                if (v == 1 || v == 2 || v == 4 || v == 8) { ++k; continue; }
-                uint32_t run = 1;
-                while (k + run < L && (src[k + run] & 15u) == v && run < 255) ++run;
-                if (k >= 1 && k <= 15) ok = false;
-                if (k == 0 && run > 1) ok = false;
-                if (last_set != v && (int)k - last_end < 16) ok = false;
-                exc.push_back(k | (run << 16) | (v << 24));
-                last_end = (int)(k + run); last_set = v;
-                k += run;
-            }
-            if (exc.size() - first_range > (size_t)EXC_MAX) ok = false;
-            if (!ok) exc.resize(first_range);
+            uint8_t gap = 0;
+            for (uint32_t k = 0; k < L; ++k) gap |= (uint8_t)((src[k] & 15u) == 0);
+            ok = gap == 0;
             any_sparse = any_sparse || ok;
         }
         fastok[s] = ok ? 1 : 0;

@@ -55,7 +55,7 @@ struct SeqStore {
     uint32_t n_seq;
 };
 
-struct Scoring { int match, mismatch, go, ge; int bias16 = 0; };   // bias16: see duo_row (s16x2 kernels only)
+struct Scoring { int match, mismatch, go, ge; int bias16 = 0; int one = 1; };   // bias16: see duo_row (s16x2 kernels only); one: fma_add
 
 struct PairSource {
     uint64_t first;          // triangle mode: global index of element 0

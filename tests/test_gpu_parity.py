@@ -117,10 +117,19 @@ def test_all_pairs_iupac_and_gaps(gpu, oracle, iupac, gaps, lo, hi, n, seed):
 
 
 def test_mixed_pure_and_ambiguous(gpu, oracle):
-    """Pure pairs run on the 2-bit kernel, the rest are deferred to the general kernel in the same call."""
+    """Pure pairs run on the 2-bit (PRMT) form of the s16x2 kernel, pairs with IUPAC codes on its 4-bit-set form in the
+    same call; only a gap character sends a pair to the general int32 kernel."""
     _, a = synth.make_random(12, 11, 40, 700)
     _, b = synth.make_random(12, 12, 40, 700, iupac=0.03)
     enc = [gpu.encode("N" + synth.to_text(s)) for pair in zip(a, b) for s in pair]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] == 0.0 and t["kernel_launches"] == 2
+    _same(got, _oracle_all(oracle, enc))
+    _, c = synth.make_random(4, 13, 40, 700, iupac=0.03, gaps=0.02)
+    enc += [gpu.encode("N" + synth.to_text(s)) for s in c]
+    enc = [e if len(e) else np.array([1], dtype=np.uint8) for e in enc]
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     t = gpu.timing()
@@ -146,10 +155,9 @@ def _sparse_ambiguous(rng, base, n_ranges, first=False):
 
 
 def test_sparse_ambiguity_codes_stay_on_the_s16x2_kernel(gpu, oracle):
-    """Sequences whose IUPAC codes are sparse (ranges of one code, different codes >= 16 apart, none at positions
-    1..15) run on the s16x2 kernel: row tables by 4-bit set, lane-specific table entries for ambiguous columns.
-    Runs of N that span several lanes, an ambiguous first base, ambiguous rows and columns meeting, every strip
-    position, short partners, and a pair above the 16-bit limit (floating window + ambiguity)."""
+    """Sequences with sparse IUPAC codes on the 4-bit-set form of the s16x2 kernel: runs of N that span several lanes,
+    an ambiguous first base, ambiguous rows and columns meeting, every strip position, short partners, and a pair
+    above the 16-bit limit (floating window + ambiguity)."""
     rng = np.random.default_rng(4242)
     root = synth.BASES[rng.integers(0, 4, size=1800)]
     enc = []
@@ -181,20 +189,61 @@ def test_sparse_ambiguity_codes_stay_on_the_s16x2_kernel(gpu, oracle):
     assert gpu.align_pairs(ab[:, 0], ab[:, 1]).tobytes() == got.tobytes()
 
 
-def test_dense_ambiguity_codes_go_to_the_general_kernel(gpu, oracle):
-    """Codes that break the sparsity rule (two different ones 5 apart; one at position 3; a gap character)."""
+def test_dense_ambiguity_codes_stay_on_the_s16x2_kernel(gpu, oracle):
+    """Any density of IUPAC codes runs on the 4-bit-set form of the s16x2 kernel (every code, neighbouring different
+    codes, codes in the first positions, all-N and all-ambiguous sequences, 1-base sequences, lengths around the strip
+    and pass widths, odd / even row counts); a gap character alone sends a pair to the general int32 kernel."""
     rng = np.random.default_rng(5)
     base = synth.BASES[rng.integers(0, 4, size=400)]
     a = base.copy(); a[100] = ord("R"); a[105] = ord("Y")
     b = base.copy(); b[3] = ord("N")
-    c = base.copy(); c[200] = ord("N"); c[300] = ord("N")          # fine
+    c = base.copy(); c[200] = ord("N"); c[300] = ord("N")
     enc = [synth.to_masks(x) for x in (a, b, c, base)]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] == 0.0 and t["dp_fast_ms"] == 0.0
+    _same(got, _oracle_all(oracle, enc))
     enc.append(gpu.encode("N" + synth.to_text(base[:150]) + "-" + synth.to_text(base[150:300])))
     gpu.upload(enc)
     got = gpu.align_all_pairs()
     t = gpu.timing()
     assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] > 0
     _same(got, _oracle_all(oracle, enc))
+    # dense random codes, all lengths
+    amb = np.frombuffer(b"ACGTRYSWKMBDHVN", dtype=np.uint8)
+    enc = [synth.to_masks(amb[rng.integers(0, len(amb), size=int(L))]) for L in
+           (1, 2, 3, 11, 12, 13, 24, 25, 383, 384, 385, 386, 700, 767, 768, 769, 1153, 40, 97)]
+    enc.append(np.full(300, 15, dtype=np.uint8))                    # all N: every cell a match
+    enc.append(synth.to_masks(np.frombuffer(b"RY" * 200, dtype=np.uint8)))   # R/Y alternating: never intersect each other
+    _, rel = synth.make_random(6, 77, 200, 900, iupac=0.3)
+    enc += [gpu.encode("N" + synth.to_text(s)) for s in rel]
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] == 0.0 and t["dp_fast_ms"] == 0.0
+    _same(got, _oracle_all(oracle, enc))
+    # sub-ranges of the triangle (a half-wanted work item mirrors its other half) and other scoring parameters
+    half = gpu.num_pairs() // 2
+    assert gpu.align_all_pairs(3, half).tobytes() == got[3:3 + half].tobytes()
+    for sc in (dict(match=5, mismatch=-4, gap_open=-10, gap_ext=-2), dict(match=3, mismatch=1, gap_open=-7, gap_ext=-1),
+               dict(match=2, mismatch=-9, gap_open=0, gap_ext=0), dict(match=-1, mismatch=-3, gap_open=-4, gap_ext=-2)):
+        got = gpu.align_all_pairs(**sc)
+        _same(got, _oracle_all(oracle, enc, match=sc["match"], mismatch=sc["mismatch"], go=sc["gap_open"], ge=sc["gap_ext"]))
+    # long ambiguous pairs: floating window on the set form
+    _, longs = synth.make_long(3, 98, length=5600, spread=0.1, div_lo=0.0, div_hi=0.08)
+    enc = []
+    for s in longs:
+        s = s.copy()
+        k = rng.random(len(s)) < 0.05
+        s[k] = amb[rng.integers(4, len(amb), size=int(k.sum()))]
+        enc.append(synth.to_masks(s))
+    enc.append(enc[0][:1000].copy())
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_general_ms"] == 0.0 and t["dp_fast_ms"] == 0.0
+    _same(got, _oracle_all(oracle, enc, threads=8))
 
 
 def test_other_scoring_parameters(gpu, oracle):

@@ -1,12 +1,16 @@
 #!/usr/bin/env python3
 """Print the instruction mix of the hottest loop of one kernel in a cubin/.so.
 
-usage: sass_loop.py <file> <kernel-name-substring> [marker-mnemonic]
+usage: sass_loop.py <file> <kernel-name-substring> [marker-mnemonic] [--count=N] [-v]
 The hot loop is taken as the innermost backward branch whose body contains the
 most occurrences of `marker` (default VIMNMX3)."""
 import re, subprocess, sys, collections
 path, pat = sys.argv[1], sys.argv[2]
-marker = sys.argv[3] if len(sys.argv) > 3 else "VIMNMX3"
+marker = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("-") else "VIMNMX3"
+want_cnt = None          # --count N: pick the (smallest) loop with exactly N markers instead of the one with the most
+for a in sys.argv:
+    if a.startswith("--count="):
+        want_cnt = int(a.split("=")[1])
 txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
 body = None
@@ -33,6 +37,8 @@ for k, (a, t) in enumerate(ins):
             lo = addr_idx[tgt]
             cnt = sum(1 for _, tt in ins[lo:k + 1] if re.search(r"\b%s\b" % re.escape(marker), tt.split()[0] if not tt.startswith("@") else tt.split()[1]))
             size = k + 1 - lo
+            if want_cnt is not None and cnt != want_cnt:
+                continue
             if cnt and (best is None or cnt > best[0] or (cnt == best[0] and size < best[1])):
                 best = (cnt, size, lo, k)
 if best is None:
