@@ -64,13 +64,12 @@ struct Device {
     size_t deferred_cap = 0;
     unsigned long long *row_items = nullptr;  // items (pairs of pairs) in rows before a; n_seq+1 entries
     size_t cap_row_items = 0, cap_p2 = 0, cap_p4 = 0, cap_off2 = 0, cap_off4 = 0, cap_len = 0, cap_pure = 0, cap_bbuf = 0;
-    uint8_t *fastok = nullptr;                // pure, or sparse ambiguity codes (s16x2 AMB variant)
-    uint32_t *exc = nullptr, *exc_off = nullptr;
-    size_t cap_fastok = 0, cap_exc = 0, cap_exc_off = 0;
+    uint8_t *fastok = nullptr;                // no gap character: the sequence can run on the s16x2 kernels
+    size_t cap_fastok = 0;
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
-    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_duo_amb = 0, grid_sets = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
+    int grid_duo = 0, grid_duo3 = 0, grid_duo8 = 0, grid_duo_auto = 0, grid_sets = 0, grid_fast = 0, grid_cta = 0, grid_gen = 0, grid_stats = 0;
     pa_pair_result *d_out[2] = {nullptr, nullptr};
     size_t d_out_cap = 0;
     pa_pair_result *h_stage[2] = {nullptr, nullptr};
@@ -152,9 +151,9 @@ struct Context {
     std::vector<uint8_t> host_pure;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
-    bool all_fast = true;              // every sequence is pure or has only sparse ambiguity codes
-    bool any_sparse = false;           // ... and at least one is of the second kind
-    bool no_amb = false;               // PAIRALIGN_NO_AMB=1: ambiguity codes always take the general kernel (tuning, tests)
+    bool all_fast = true;              // no sequence holds a gap character (everything can run on the s16x2 kernels)
+    bool any_sparse = false;           // at least one gap-free sequence has IUPAC ambiguity codes (set form of the s16x2 kernel)
+    bool no_amb = false;               // PAIRALIGN_NO_AMB=1: ambiguity codes always take the general int32 kernel (comparison, tests)
     bool force_32bit = false;          // PAIRALIGN_FORCE_32BIT=1: skip the s16x2 kernel (testing / comparison)
     int kduo = 0;                      // strip width of the s16x2 kernel; 0: per work item (duo_pick_k)
     int kduo_forced = 0;               // PAIRALIGN_KDUO=8|12 forces one width (tuning)
@@ -176,7 +175,7 @@ void free_device(Device &d) {
     if (d.id < 0) return;
     cudaSetDevice(d.id);
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
-    cudaFree(d.fastok); cudaFree(d.exc); cudaFree(d.exc_off);
+    cudaFree(d.fastok);
     cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3); cudaFree(d.bbuf);
     cudaFree(d.row_items); cudaFree(d.raw); cudaFree(d.raw_off);
     for (auto &c : d.ce) { for (auto &e : c.k) if (e) cudaEventDestroy(e); if (c.done) cudaEventDestroy(c.done); }
@@ -192,7 +191,7 @@ void free_device(Device &d) {
 SeqStore store_of(const Device &d, uint32_t n_seq) {
     SeqStore s;
     s.p2 = d.p2; s.p4 = d.p4; s.off2 = d.off2; s.off4 = d.off4; s.len = d.len; s.pure = d.pure; s.n_seq = n_seq;
-    s.fastok = d.fastok; s.exc = d.exc; s.exc_off = d.exc_off;
+    s.fastok = d.fastok;
     return s;
 }
 
@@ -616,9 +615,6 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
         d.grid_duo_auto = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<-1>, WARPS_PER_CTA * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<-1, 1, -1>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo_amb = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1>, WARPS_PER_CTA * 32, 0);
         d.grid_sets = std::max(1, std::min(occ, occ_c)) * d.n_sm;
@@ -630,7 +626,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_duo_amb), d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -761,7 +757,6 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         CU(grow((void **)&d.len, d.cap_len, nidx * 4));
         CU(grow((void **)&d.pure, d.cap_pure, nidx));
         CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
-        CU(grow((void **)&d.exc_off, d.cap_exc_off, (nidx + 1) * 4));
         CU(grow((void **)&d.raw, d.cap_raw, (size_t)std::max<uint64_t>(n_bases, 16)));
         CU(grow((void **)&d.raw_off, d.cap_raw_off, (nidx + 1) * sizeof(unsigned long long)));
         d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
@@ -786,7 +781,6 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     // Meanwhile on the host: which sequences are plain A/C/G/T and which of the others are free of gap characters
     // (branch-free scans the compiler vectorises).
     std::vector<uint8_t> pure(n_seq), fastok(n_seq);
-    std::vector<uint32_t> exc, exc_off((size_t)n_seq + 1, 0);
     bool all_fast = true, all_pure = true, any_sparse = false;
     for (uint32_t s = 0; s < n_seq; ++s) {
         const uint8_t *src = c.host_masks + c.host_offsets[s];
@@ -799,7 +793,6 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         const bool pr = bad == 0;
         pure[s] = pr ? 1 : 0;
         all_pure = all_pure && pr;
-        exc_off[s] = 0;
         // an ambiguous sequence stays on the s16x2 path (4-bit-set variant) unless it holds a gap character: '-' scores
         // INT_MIN with 32-bit wrap-around in the reference (src/seqpair.cpp:192-193), which only the int32 kernel reproduces
         bool ok = true;
@@ -812,7 +805,6 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         fastok[s] = ok ? 1 : 0;
         all_fast = all_fast && ok;
     }
-    exc_off[n_seq] = (uint32_t)exc.size();
     c.n_seq = n_seq;
     c.host_pure = pure;
     c.len = len;
@@ -830,12 +822,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     }
     for (auto &d : c.dev) {
         CU(cudaSetDevice(d.id));
-        CU(grow((void **)&d.exc, d.cap_exc, std::max<size_t>(exc.size(), 1) * 4));
         if (n_seq) {
             // d.pure was written by pa_pack_kernel from the same bytes; the host's copy is what launch decisions use
             CU(cudaMemcpyAsync(d.fastok, fastok.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.exc_off, exc_off.data(), ((size_t)n_seq + 1) * 4, cudaMemcpyHostToDevice, d.stream));
-            if (!exc.empty()) CU(cudaMemcpyAsync(d.exc, exc.data(), exc.size() * 4, cudaMemcpyHostToDevice, d.stream));
         }
     }
     for (auto &d : c.dev) {       // the host vectors above die at return

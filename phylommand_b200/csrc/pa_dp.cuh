@@ -49,9 +49,7 @@ struct SeqStore {
     const uint32_t *off4;    // word offset of sequence s in p4
     const uint32_t *len;     // encoded length
     const uint8_t  *pure;    // 1 if the sequence holds only A/C/G/T
-    const uint8_t  *fastok;  // 1 if pure, or if its IUPAC ambiguity codes are sparse enough for the s16x2 kernel (exc)
-    const uint32_t *exc;     // ambiguity ranges of all sequences: pos (16 bits) | run << 16 (8 bits) | set << 24 (4 bits)
-    const uint32_t *exc_off; // ranges of sequence s: exc[exc_off[s] .. exc_off[s+1])
+    const uint8_t  *fastok;  // 1 if the sequence holds no gap character: plain, or IUPAC codes for the 4-bit-set s16x2 kernel
     uint32_t n_seq;
 };
 
@@ -426,45 +424,11 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
 constexpr int WIN_T = 8192, WIN_Q = 4096;
 constexpr int WIN_BIAS = -16384;     // centre of the window in stored terms: values stay in about [-29000, -3800]
 
-// AMB (sparse IUPAC ambiguity codes, no gaps): the 2-bit sequences hold a placeholder base at ambiguous positions and
-// the ranges of such positions travel beside them (ex, ey1, ey2: pos | run << 16 | set << 24, in shared memory).
-// Rows: the row tables are indexed by the row's 4-bit SET (16 x 2 entries) instead of its base code.  Columns: the two
-// table entries that serve column 0 of pair 1 / pair 2 (4 and 6; increments 4 and 7) become LANE-specific -- a lane
-// uses them for its ambiguous columns (all of one set: the host only admits sequences whose different sets are at
-// least 16 apart and whose positions 1..15 are plain) or for column 0, and computes their two bytes per row from
-// (row set & column set).  Everything else -- recurrence, selectors, pads -- is the plain kernel.
-constexpr int EXC_MAX = 64;      // ambiguity ranges per sequence the s16x2 kernel takes
-__device__ __forceinline__ uint32_t exc_set_at(const uint32_t *e, const int ne, const int j) {
-    uint32_t m = 0;
-    for (int q = 0; q < ne; ++q) {
-        const uint32_t w = e[q];
-        const int pos = (int)(w & 0xffffu), run = (int)((w >> 16) & 0xffu);
-        if (j >= pos && j < pos + run) m = (w >> 24) & 15u;
-    }
-    return m;
-}
-
-// (Rlo, Rhi, Mlo, Mhi) of one row for one lane: entries 0-3 from the shared table of the row's set, the special
-// entries 4 / 6 (scores) and 4 / 7 (mismatch flags) from (row set & the lane's column sets).
-__device__ __forceinline__ int4 amb_row_table(const int4 *tab, const Scoring sc, const uint32_t rowset, const bool row0,
-                                              const uint32_t a1, const uint32_t a2, const bool spgo1, const bool spgo2) {
-    const int4 T = tab[(row0 ? 16 : 0) + rowset];
-    const bool f1 = (rowset & a1) != 0, f2 = (rowset & a2) != 0;
-    const int s1 = (f1 ? sc.match : sc.mismatch) + ((spgo1 || row0) ? sc.go : 0);
-    const int s2 = (f2 ? sc.match : sc.mismatch) + ((spgo2 || row0) ? sc.go : 0);
-    const uint32_t Rhi = ((uint32_t)s1 & 0xffu) | (((uint32_t)s2 & 0xffu) << 16);
-    const uint32_t Mhi = (f1 ? 0u : 1u) | 0x00010000u | (f2 ? 0u : 0x01000000u);
-    return make_int4(T.x, (int)Rhi, T.z, (int)Mhi);
-}
-
-template <int K, bool WIN = false, bool AMB = false, int GEC = 0>
+template <int K, bool WIN = false, int GEC = 0>
 __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
                                                const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
                                                const uint32_t vrow, int4 *tab,
-                                               pa_pair_result *res1, pa_pair_result *res2, const int lane,
-                                               const uint32_t *ex = nullptr, const int nx = 0,
-                                               const uint32_t *ey1 = nullptr, const int ny1 = 0,
-                                               const uint32_t *ey2 = nullptr, const int ny2 = 0) {
+                                               pa_pair_result *res1, pa_pair_result *res2, const int lane) {
     constexpr int W = 32 * K;
     const int mmax = m1 > m2 ? m1 : m2;
     const int P = (mmax + W - 1) / W;
@@ -485,19 +449,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
 
     const uint32_t y10 = fetch2(ys1, 0), y20 = fetch2(ys2, 0);
     {   // score / increment tables of this (x, y1, y2): one entry per row code and row-0 flag
-        if (AMB) {      // entry z * 16 + row set: bases 0-3 against the set; the special entries are made per lane and row
-            const uint32_t xm = lane & 15u, z = lane >> 4;
-            const int adj = z ? sc.go : 0;
-            const uint32_t Mb = (uint32_t)(sc.match + adj) & 0xffu, Xb = (uint32_t)(sc.mismatch + adj) & 0xffu;
-            uint32_t r = 0, f = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool hit = (xm >> c) & 1u;
-                r |= (hit ? Mb : Xb) << (8 * c);
-                f |= (hit ? 0u : 1u) << (8 * c);
-            }
-            tab[lane] = make_int4((int)r, 0, (int)f, 0x00010000);
-        } else if (lane < 8) {
+        if (lane < 8) {
             const uint32_t xi = lane & 3u, z = lane >> 2;
             const int adj = z ? sc.go : 0;
             const uint32_t Mb = (uint32_t)(sc.match + adj) & 0xffu, Xb = (uint32_t)(sc.mismatch + adj) & 0xffu;
@@ -524,8 +476,6 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
         const int s0 = p * W + lane * K;           // slot of this lane's k = 0
         // X: the odd row (2u-1, then 2u+1), Y: the even row 2u
         uint32_t HX[K], HY[K], Gy[K], C1X[K], C1Y[K], C2X[K], C2Y[K], selS[K], selI1[K], selI2[K];
-        uint32_t a1 = 0, a2 = 0;             // AMB: set behind this lane's special entries (pair 1, pair 2)
-        bool spgo1 = false, spgo2 = false;   // ... which belong to column 0 (gap-open adjustment on every row)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j1 = s0 + k - pad1, j2 = s0 + k - pad2;
@@ -537,18 +487,6 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             if (j2 < 0)       { c2 = 5; i2 = 0x5555u; }
             else if (j2 == 0) { c2 = 6; i2 = 0x5657u; }
             else              { c2 = fetch2(ys2, j2); i2 = 0x5650u | c2; }
-            if (AMB) {   // ambiguous columns use this lane's special entries, like column 0
-                if (j1 >= 0) {
-                    const uint32_t am = ny1 ? exc_set_at(ey1, ny1, j1) : 0u;
-                    if (j1 == 0) { a1 = am ? am : (1u << y10); spgo1 = true; }
-                    else if (am) { a1 = am; c1 = 4; i1 = 0x5654u; }
-                }
-                if (j2 >= 0) {
-                    const uint32_t am = ny2 ? exc_set_at(ey2, ny2, j2) : 0u;
-                    if (j2 == 0) { a2 = am ? am : (1u << y20); spgo2 = true; }
-                    else if (am) { a2 = am; c2 = 6; i2 = 0x5657u; }
-                }
-            }
             selS[k] = ((8u | c2) << 12) | (c2 << 8) | ((8u | c1) << 4) | c1;
             selI1[k] = i1; selI2[k] = i2;
         }
@@ -593,20 +531,8 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
             if (iA >= 0 && iA < n) {
                 const bool store = (lane == 31) && !last_pass;
-                uint32_t mA = 0, mB = 0;     // AMB: the sets of rows iA and iA + 1
-                if (AMB) {
-                    mA = 1u << (xi2 & 3u); mB = 1u << (xi2 >> 2);
-                    for (int q = 0; q < nx; ++q) {
-                        const uint32_t w = ex[q];
-                        const int pos = (int)(w & 0xffffu), end = pos + (int)((w >> 16) & 0xffu);
-                        if (iA >= pos && iA < end) mA = (w >> 24) & 15u;
-                        if (iA + 1 >= pos && iA + 1 < end) mB = (w >> 24) & 15u;
-                    }
-                }
                 {   // even row iA: previous row in X, result in Y
-                    int4 T;
-                    if (AMB) T = amb_row_table(tab, sc, mA, iA == 0, a1, a2, spgo1, spgo2);
-                    else T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
+                    const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
                     duo_row<K, GEC>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
                                (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
                                hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
@@ -630,9 +556,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                     }
                 }
                 if (iA + 1 < n) {   // odd row iA+1: previous row in Y, result in X
-                    int4 T;
-                    if (AMB) T = amb_row_table(tab, sc, mB, false, a1, a2, spgo1, spgo2);
-                    else T = tab[xi2 >> 2];
+                    const int4 T = tab[xi2 >> 2];
                     duo_row<K, GEC>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
                                (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
                                hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
@@ -821,8 +745,7 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
                    const uint32_t kmask = DUO_KSET, const int step_cost = DUO_STEP_COST, const int win_ok = 0,
                    const int amb_launch = 0) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
-    __shared__ int4 tabs[WARPS_PER_CTA][K < 0 ? 32 : 8];
-    __shared__ uint32_t excs[K < 0 ? WARPS_PER_CTA : 1][3][EXC_MAX];   // ambiguity ranges of x, y1, y2 (K = -1 kernel)
+    __shared__ int4 tabs[WARPS_PER_CTA][8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
@@ -853,19 +776,15 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         const int n = (int)S.len[a], m1 = (int)S.len[b1], m2 = (int)S.len[b2];
         // pairs this path cannot take go to the general / 32-bit kernels
         // longer than max_len16: floating-window variant (K = 0 kernel, when the host allows it), else deferred
-        const uint32_t lim = (K <= 0 && win_ok) ? 0xffffffffu : max_len16;
-        // sequences with sparse IUPAC ambiguity codes (fastok, not pure): their items belong to the K = -1 launch (AMB
-        // variant) when the host runs one (amb_launch); each item is done by exactly one of the two launches, and
-        // only the K = 0 launch defers
-        const uint8_t *good = (K <= 0 && amb_launch) ? S.fastok : S.pure;
+        const uint32_t lim = (K == 0 && win_ok) ? 0xffffffffu : max_len16;
+        // sequences with IUPAC ambiguity codes but no gap character (fastok, not pure): their items belong to the launch
+        // of the 4-bit-set form (pa_warp_sets_kernel) when the host runs one (amb_launch); each item is done by exactly
+        // one of the two launches, and only this one defers
+        const uint8_t *good = (K == 0 && amb_launch) ? S.fastok : S.pure;
         const bool okx = good[a] && n > 0 && (uint32_t)n <= lim;
         const bool ok1 = okx && good[b1] && m1 > 0 && (uint32_t)m1 <= lim;
         const bool ok2 = okx && good[b2] && m2 > 0 && (uint32_t)m2 <= lim;
-        if (K < 0) {
-            use1 = use1 && ok1; use2 = use2 && ok2;
-            if (!use1 && !use2) continue;
-        }
-        if (K >= 0 && lane == 0) {
+        if (lane == 0) {
             if (use1 && !ok1) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 - first);
             if (use2 && !ok2) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 + 1 - first);
         }
@@ -875,9 +794,8 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         // a half that is not wanted mirrors the other one
         const uint32_t y1 = use1 ? b1 : b2, y2 = use2 ? b2 : b1;
         const int my1 = use1 ? m1 : m2, my2 = use2 ? m2 : m1;
-        // items with an ambiguous (fastok, not pure) sequence are the K = -1 launch's, all others the K >= 0 launch's
-        const bool amb_item = !(S.pure[a] && S.pure[y1] && S.pure[y2]);
-        if ((K < 0) != amb_item) continue;
+        // items with an ambiguous (fastok, not pure) sequence are the set-form launch's
+        if (!(S.pure[a] && S.pure[y1] && S.pure[y2])) continue;
         __syncwarp();
         const uint32_t *xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
         const uint32_t *ys1 = stage_seq(S.p2 + S.off2[y1], (uint32_t)(my1 + 15) >> 4, stage[wib][1], lane);
@@ -886,38 +804,22 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
         // y1 / y2 / my1 / my2: what is actually aligned (a half that is not wanted mirrors the other one)
         const bool too_long = (uint32_t)n > max_len16 || (uint32_t)my1 > max_len16 || (uint32_t)my2 > max_len16;
-        if constexpr (K < 0) {
-            // ambiguity ranges next to the 2-bit sequences
-            const uint32_t e0 = S.exc_off[a], e1 = S.exc_off[y1], e2 = S.exc_off[y2];
-            const int nx = (int)(S.exc_off[a + 1] - e0), ny1 = (int)(S.exc_off[y1 + 1] - e1), ny2 = (int)(S.exc_off[y2 + 1] - e2);
-            for (int q = lane; q < EXC_MAX; q += 32) {
-                if (q < nx) excs[wib][0][q] = S.exc[e0 + q];
-                if (q < ny1) excs[wib][1][q] = S.exc[e1 + q];
-                if (q < ny2) excs[wib][2][q] = S.exc[e2 + q];
-            }
-            __syncwarp();
-            if (too_long)
-                align_warp_duo<12, true, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane,
-                                               excs[wib][0], nx, excs[wib][1], ny1, excs[wib][2], ny2);
-            else
-                align_warp_duo<12, false, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane,
-                                                excs[wib][0], nx, excs[wib][1], ny1, excs[wib][2], ny2);
-        } else if constexpr (K == 0) {
+        if constexpr (K == 0) {
             if (too_long) {
                 // bbuf rows come in pairs here (values, offsets); the virtual-column row is the last pair
-                align_warp_duo<12, true, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane);
+                align_warp_duo<12, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, tabs[wib], r1, r2, lane);
                 continue;
             }
             // strip width per work item: the fewest issue slots for these lengths (duo_pick_k)
             switch (duo_pick_k(my1 > my2 ? my1 : my2, kmask & DUO_KSET, step_cost)) {
-                case 8:  align_warp_duo<8, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 10: align_warp_duo<10, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 11: align_warp_duo<11, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                case 12: align_warp_duo<12, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
-                default: align_warp_duo<DUO_KMAX, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 8:  align_warp_duo<8, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 10: align_warp_duo<10, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 11: align_warp_duo<11, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                case 12: align_warp_duo<12, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
+                default: align_warp_duo<DUO_KMAX, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane); break;
             }
         } else {
-            align_warp_duo<K, false, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane);
+            align_warp_duo<K, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, tabs[wib], r1, r2, lane);
         }
     }
 }
