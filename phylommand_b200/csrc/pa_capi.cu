@@ -4,6 +4,7 @@
 #include "pa_dp.cuh"
 #include "pa_dp32.cuh"
 #include "pa_dp_sets.cuh"
+#include "pa_dp_moves.cuh"
 #include "pa_peak.cuh"
 
 #include <algorithm>
@@ -80,7 +81,9 @@ struct Device {
     unsigned long long *d_dirs_off = nullptr, *d_ops_off = nullptr;
     uint32_t *d_nops = nullptr;
     pa_pair_result *d_res = nullptr;
-    size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0;
+    size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0, cap_items = 0;
+    uint2 *d_items = nullptr;                 // work items of the move-storing s16x2 kernels (entries of the batch, in twos)
+    int grid_moves_warp = 0, grid_moves_cta = 0;
     // Events of one in-flight chunk (two chunks are in flight: slot = chunk & 1).  k[0]..k[1] s16x2 stage,
     // k[1]..k[2] 32-bit warp stage, k[2]..k[3] CTA-per-pair stage, k[3]..k[4] general stage; k[4] also releases the
     // D2H copy of the chunk on copy_stream, `done` marks its end (and lets the next kernel reuse d_out[slot]).
@@ -181,7 +184,7 @@ void free_device(Device &d) {
     for (auto &c : d.ce) { for (auto &e : c.k) if (e) cudaEventDestroy(e); if (c.done) cudaEventDestroy(c.done); }
     for (int k = 0; k < 2; ++k) { cudaFree(d.d_out[k]); if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]); }
     cudaFree(d.d_ia); cudaFree(d.d_ib);
-    cudaFree(d.d_dirs); cudaFree(d.d_ops); cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
+    cudaFree(d.d_dirs); cudaFree(d.d_ops); cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res); cudaFree(d.d_items);
     for (auto &e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
@@ -618,6 +621,12 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1>, WARPS_PER_CTA * 32, 0);
         d.grid_sets = std::max(1, std::min(occ, occ_c)) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
+        d.grid_moves_warp = std::max(1, std::min(occ, occ_c)) * d.n_sm;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, 0);
+        d.grid_moves_cta = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
@@ -626,7 +635,7 @@ int pa_init(const int *devices, int n_dev) {
         d.grid_gen = std::max(1, occ) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(d.grid_fast, d.grid_gen)) * WARPS_PER_CTA, d.grid_cta);
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, d.grid_moves_warp), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
         if (e2 != cudaSuccess) {
             std::string msg = cudaGetErrorString(e2);
             for (auto &dd : c->dev) free_device(dd);
@@ -960,36 +969,45 @@ int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t 
 
 // Bytes of the move store of one pair: n rows of P*W/4 bytes (W = 32*K slots per block), 128-byte aligned.
 static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool pure, bool fast) {
-    const uint64_t W = 32ull * ((pure && fast) ? KFAST : KGEN);
+    const uint64_t W = 32ull * ((pure && fast) ? KMOV : KGEN);
     const uint64_t P = (m + W - 1) / W;
     const uint64_t bytes = (uint64_t)n * (P * W / 4);
     return (bytes + 127) / 128 * 128;
 }
 
-// pairalign -a on one device: pairs [lo, hi) of the caller's list in batches sized to the move store.
-// Long A/C/G/T pairs take a CTA each (pa_cta32_kernel<KFAST, true>) when a batch holds too few of them to keep a
-// one-pair-per-warp kernel busy -- which the size of their move stores (2 bits per cell: 226 MB for 30 kb x 30 kb)
-// all but guarantees.
+// pairalign -a on one device: pairs [lo, hi) of the caller's list in batches sized to the move store (2 bits per
+// cell).  A/C/G/T pairs run on the s16x2 move-storing kernels (pa_dp_moves.cuh), two list entries that share their
+// first sequence per work item; pairs longer than LONG_LEN take a CTA per item when a batch holds too few of them to
+// fill a warp-per-item grid -- which the size of their move stores (226 MB for 30 kb x 30 kb) all but guarantees.
+// Everything else (IUPAC codes, gap characters, scoring outside the byte tables) runs on the general int32 kernel.
 static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t *ia, const uint32_t *ib, uint64_t lo, uint64_t hi,
                      uint8_t *ops, const uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res, double *kernel_ms) {
     if (lo >= hi) return PA_OK;
     CU(cudaSetDevice(d.id));
-    const bool fast = fast_params_ok(prm);
+    int bias16 = 0;
+    const uint32_t l16 = fast_params_ok(prm) ? max_len16(prm, &bias16) : 0;
+    const long long win_spread = 17ll * (std::llabs((long long)prm.match) + std::llabs((long long)prm.mismatch) +
+                                         std::llabs((long long)prm.gap_open) + std::llabs((long long)prm.gap_ext));
+    const bool win_ok = prm.gap_ext >= -1024 && win_spread <= 3500;
+    // the s16x2 move kernels take the A/C/G/T pairs of this call (else: everything on the general kernel)
+    const bool fast = l16 >= 16 && (c.max_len <= l16 || win_ok) && !c.force_32bit;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = std::min<uint64_t>((uint64_t)((free_b + d.cap_dirs) / 2), 72ull << 30);
-    const Scoring sc{prm.match, prm.mismatch, prm.gap_open, prm.gap_ext};
+    Scoring sc{prm.match, prm.mismatch, prm.gap_open, prm.gap_ext};
+    sc.bias16 = bias16;
     const SeqStore S = store_of(d, c.n_seq);
     const int threads = WARPS_PER_CTA * 32;
     std::vector<unsigned long long> h_dirs_off, h_ops_off;
-    std::vector<uint32_t> h_long;
+    std::vector<uint2> h_items, h_items_long;
+    const uint64_t wave_pairs = 2ull * (uint64_t)d.grid_moves_cta;       // one wave of the CTA-per-item grid
     uint64_t s0 = lo;
     while (s0 < hi) {
         // one batch: as many pairs as the move store holds
-        uint64_t e0 = s0, dbytes = 0, obytes = 0;
+        uint64_t e0 = s0, dbytes = 0, obytes = 0, n_long = 0;
         uint64_t ck_e0 = s0, ck_dbytes = 0, ck_obytes = 0;      // the batch as it was after the last whole wave of long pairs
-        bool any_pure = false, any_general = false;
-        h_dirs_off.clear(); h_ops_off.clear(); h_long.clear();
+        bool any_general = false;
+        h_dirs_off.clear(); h_ops_off.clear();
         while (e0 < hi && e0 - s0 < (1ull << 20)) {
             const uint32_t a = ia[e0], b = ib[e0];
             const bool pure = c.host_pure[a] && c.host_pure[b];
@@ -997,10 +1015,10 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             if (dbytes + need > budget) {
                 if (e0 == s0) return fail(PA_ENOMEM, "the moves of pair %llu need %llu bytes; %llu available", (unsigned long long)e0,
                                           (unsigned long long)need, (unsigned long long)budget);
-                // a batch of long pairs runs one pair per CTA: end it on a whole number of waves of the persistent grid
-                if (h_long.size() == e0 - s0 && ck_e0 > s0 && !c.no_cta) {
+                // a batch of long pairs runs one item per CTA: end it on a whole number of waves of the persistent grid
+                if (n_long == e0 - s0 && ck_e0 > s0 && !c.no_cta) {
                     e0 = ck_e0; dbytes = ck_dbytes; obytes = ck_obytes;
-                    h_dirs_off.resize(e0 - s0); h_ops_off.resize(e0 - s0); h_long.resize(e0 - s0);
+                    h_dirs_off.resize(e0 - s0); h_ops_off.resize(e0 - s0);
                 }
                 break;
             }
@@ -1008,16 +1026,31 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             h_ops_off.push_back(obytes);
             dbytes += need;
             obytes += (uint64_t)c.len[a] + c.len[b];
-            if (pure && fast) {
-                any_pure = true;
-                if (need && std::max(c.len[a], c.len[b]) > LONG_LEN) h_long.push_back((uint32_t)(e0 - s0));
-            } else any_general = true;
+            if (pure && fast && need) { if (std::max(c.len[a], c.len[b]) > LONG_LEN) ++n_long; }
+            else if (need) any_general = true;
             ++e0;
-            if (h_long.size() == e0 - s0 && h_long.size() % (size_t)d.grid_cta == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
+            if (n_long == e0 - s0 && n_long % wave_pairs == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
         }
         const uint64_t nb = e0 - s0;
-        const bool route_long = !h_long.empty() && !c.no_cta &&
-                                (c.force_cta || h_long.size() < 4ull * (uint64_t)d.grid_fast * WARPS_PER_CTA);
+        // work items of the s16x2 kernels: neighbouring entries with the same first sequence go together
+        h_items.clear(); h_items_long.clear();
+        n_long = 0;
+        for (uint64_t k = 0; k < nb; ++k) {
+            const uint32_t a = ia[s0 + k], b = ib[s0 + k];
+            if (!(fast && c.host_pure[a] && c.host_pure[b] && c.len[a] && c.len[b])) continue;
+            const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
+            uint32_t second = 0xffffffffu;
+            if (k + 1 < nb) {
+                const uint32_t a2 = ia[s0 + k + 1], b2 = ib[s0 + k + 1];
+                if (a2 == a && c.host_pure[b2] && c.len[b2] && (std::max(c.len[a], c.len[b2]) > LONG_LEN) == lng) second = (uint32_t)(k + 1);
+            }
+            (lng ? h_items_long : h_items).push_back(make_uint2((uint32_t)k, second));
+            if (lng) n_long += second != 0xffffffffu ? 2 : 1;
+            if (second != 0xffffffffu) ++k;
+        }
+        const bool route_long = !h_items_long.empty() && !c.no_cta &&
+                                (c.force_cta || h_items_long.size() < 4ull * (uint64_t)d.grid_moves_warp * WARPS_PER_CTA);
+        if (!route_long) { h_items.insert(h_items.end(), h_items_long.begin(), h_items_long.end()); h_items_long.clear(); }
         auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
             if (bytes <= cap && *ptr) return cudaSuccess;
             cudaFree(*ptr); *ptr = nullptr; cap = 0;
@@ -1027,6 +1060,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         };
         CU(grow((void **)&d.d_dirs, d.cap_dirs, std::max<uint64_t>(dbytes, 128)));
         CU(grow((void **)&d.d_ops, d.cap_ops, std::max<uint64_t>(obytes, 128)));
+        CU(grow((void **)&d.d_items, d.cap_items, std::max<size_t>(h_items.size() + h_items_long.size(), 1) * sizeof(uint2)));
         if (nb > d.cap_tb_pairs) {
             cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
             d.d_dirs_off = d.d_ops_off = nullptr; d.d_nops = nullptr; d.d_res = nullptr; d.cap_tb_pairs = 0;
@@ -1046,31 +1080,37 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaMemcpyAsync(d.d_ib, ib + s0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_dirs_off, h_dirs_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_ops_off, h_ops_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        if (!h_items.empty())
+            CU(cudaMemcpyAsync(d.d_items, h_items.data(), h_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, d.stream));
+        if (!h_items_long.empty())
+            CU(cudaMemcpyAsync(d.d_items + h_items.size(), h_items_long.data(), h_items_long.size() * sizeof(uint2), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
         CU(cudaMemsetAsync(d.d_res, 0, nb * sizeof(pa_pair_result), d.stream));
-        if (route_long) {
-            int rc = ensure_deferred(d, (size_t)nb);
-            if (rc) return rc;
-            const unsigned int n_long = (unsigned int)h_long.size();
-            CU(cudaMemcpyAsync(d.deferred3, h_long.data(), h_long.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.n_deferred + 2, &n_long, sizeof n_long, cudaMemcpyHostToDevice, d.stream));
-        }
         CU(cudaEventRecord(d.ev[0], d.stream));
-        if (any_pure && !(route_long && h_long.size() == nb)) {
-            pa_warp32_dirs_kernel<KFAST><<<d.grid_fast, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters, d.bbuf, d.bbuf_rows,
-                                                                                d.d_res, d.d_dirs, d.d_dirs_off,
-                                                                                route_long ? LONG_LEN : 0xffffffffu);
+        if (!h_items.empty()) {
+            if (prm.gap_ext == -1)
+                pa_warp_duo_moves_kernel<-1><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items, (uint32_t)h_items.size(), l16,
+                                                                                          d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            else
+                pa_warp_duo_moves_kernel<0><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items, (uint32_t)h_items.size(), l16,
+                                                                                         d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
             CU(cudaGetLastError());
             d.launches += 1;
         }
-        if (route_long) {
-            PairSource src;
-            src.first = 0; src.ia = d.d_ia; src.ib = d.d_ib; src.idx = d.deferred3;
-            pa_cta32_kernel<KFAST, true><<<d.grid_cta, CTA_WARPS * 32, 0, d.stream>>>(
-                S, sc, src, d.n_deferred + 2, d.counters + 3, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+        CU(cudaEventRecord(d.ev[3], d.stream));
+        if (!h_items_long.empty()) {
+            if (prm.gap_ext == -1)
+                pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, 0, d.stream>>>(
+                    S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
+                    d.d_res, d.d_dirs, d.d_dirs_off);
+            else
+                pa_cta_duo_moves_kernel<0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, 0, d.stream>>>(
+                    S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
+                    d.d_res, d.d_dirs, d.d_dirs_off);
             CU(cudaGetLastError());
             d.launches += 1;
         }
+        CU(cudaEventRecord(d.ev[4], d.stream));
         if (any_general) {
             pa_general_dirs_kernel<<<d.grid_gen, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, nb, d.counters + 1, d.bbuf, d.bbuf_rows,
                                                                          d.d_res, d.d_dirs, d.d_dirs_off, fast ? 0 : 1);
@@ -1079,7 +1119,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         }
         CU(cudaEventRecord(d.ev[1], d.stream));
         pa_walk_kernel<<<(unsigned)((nb + WALK_WARPS - 1) / WALK_WARPS), WALK_WARPS * 32, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
-                                                                        d.d_ops_off, d.d_nops, fast ? KFAST : KGEN, KGEN);
+                                                                        d.d_ops_off, d.d_nops, KMOV, KGEN);
         CU(cudaGetLastError());
         d.launches += 1;
         CU(cudaEventRecord(d.ev[2], d.stream));
@@ -1087,11 +1127,13 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaMemcpyAsync(n_ops + s0, d.d_nops, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
         if (res) CU(cudaMemcpyAsync(res + s0, d.d_res, nb * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
-        float dp_ms = 0, walk_ms = 0;
+        float dp_ms = 0, walk_ms = 0, warp_ms = 0, cta_ms = 0;
         CU(cudaEventElapsedTime(&dp_ms, d.ev[0], d.ev[1]));
         CU(cudaEventElapsedTime(&walk_ms, d.ev[1], d.ev[2]));
+        CU(cudaEventElapsedTime(&warp_ms, d.ev[0], d.ev[3]));
+        CU(cudaEventElapsedTime(&cta_ms, d.ev[3], d.ev[4]));
         kernel_ms[0] += dp_ms; kernel_ms[1] += walk_ms;
-        if (route_long) d.cta_ms += dp_ms; else d.fast_ms += dp_ms;
+        d.duo_ms += warp_ms; d.cta_ms += cta_ms; d.gen_ms += dp_ms - warp_ms - cta_ms;
         // the walk wrote each op string backwards (the reference reverses at src/seqpair.cpp:183-188)
         for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);
         s0 = e0;
@@ -1157,7 +1199,8 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
         const Device &d = c.dev[p];
         tm.kernel_ms = std::max(tm.kernel_ms, kms[2 * p] + kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
-        tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
+        tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);
+        tm.dp_general_ms = std::max(tm.dp_general_ms, d.gen_ms);
         tm.walk_ms = std::max(tm.walk_ms, kms[2 * p + 1]);
         tm.kernel_launches += d.launches;
     }

@@ -249,7 +249,7 @@ __device__ __forceinline__ void align_warp(const uint32_t *xs, const int n, cons
                             const bool pU = (gy >= gx);
                             uint32_t c = pD ? cd + inc : (pU ? cu : cl);
                             if (EDGE && selI[k] == 2) c = 0;
-                            if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
+                            if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 3u)) << (2 * k);      // bit 0: not diagonal, bit 1: left rather than up
                             Hd = H[k]; cd = cu;
                             H[k] = h; Gy[k] = gy; C[k] = c;
                             Gl = gx; cl = c;

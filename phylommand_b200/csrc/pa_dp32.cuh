@@ -44,16 +44,13 @@ __device__ __forceinline__ void build_tab32(int4 *tab, const Scoring sc, const u
     }
 }
 
-// DIRS: also return the moves of this lane's K cells, 2 bits each (0 D, 1 U, 2 L), column k in bits 2k..2k+1
-template <int K, bool DIRS = false>
+template <int K>
 __device__ __forceinline__ void row32(const int (&Hs)[K], int (&Hd)[K], int (&Gy)[K],
                                       const uint32_t (&Cs)[K], uint32_t (&Cd)[K],
                                       const uint32_t (&selS)[K], const uint32_t (&selI)[K],
                                       const uint32_t Rlo, const uint32_t Rhi, const uint32_t Mlo, const uint32_t Mhi,
                                       const int go, const int ge, int hdiag, int Gl, uint32_t cd, uint32_t cl,
-                                      int &Hout, int &Gxout, uint32_t &cout, uint32_t &moves) {
-    static_assert(!DIRS || K <= 16, "moves of one lane must fit 32 bits");
-    uint32_t mv = 0;
+                                      int &Hout, int &Gxout, uint32_t &cout) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int s = (int)prmt(Rlo, Rhi, selS[k]);
@@ -68,13 +65,11 @@ __device__ __forceinline__ void row32(const int (&Hs)[K], int (&Hd)[K], int (&Gy
         const bool pU = (gy >= gx);
         const uint32_t cdi = cd + inc;
         const uint32_t c = pD ? cdi : (pU ? cu : cl);
-        if (DIRS) mv |= (pD ? 0u : (pU ? 1u : 2u)) << (2 * k);
         hdiag = Hs[k]; cd = cu;
         Hd[k] = h; Gy[k] = gy; Cd[k] = c;
         Gl = gx; cl = c;
     }
     Hout = Hd[K - 1]; Gxout = Gl; cout = cl;
-    moves = mv;
 }
 
 // Edge policy of the warp kernel: scratch rows in global memory, no waiting.
@@ -93,7 +88,8 @@ struct GlobalEdge {
 
 // Edge policy of the CTA kernel.  Rows are counted per channel since the start of the
 // pair (every block has n rows), so ring slots and the two counters never reset.
-struct RingEdge {
+template <int RR>
+struct RingEdgeT {
     // input side
     const int4 *in_ring;     // shared ring of the channel from the previous warp (nullptr: block 0 or wrap channel)
     const int4 *in_global;   // wrap channel / virtual row
@@ -109,11 +105,11 @@ struct RingEdge {
     int out_base;
 
     __device__ __forceinline__ int4 load(int row) const {
-        if (in_ring) return in_ring[(in_base + row) & (RING_ROWS - 1)];
+        if (in_ring) return in_ring[(in_base + row) & (RR - 1)];
         return __ldcg(&in_global[in_mul * row]);
     }
     __device__ __forceinline__ void store(int row, const int4 v) const {
-        if (out_ring) out_ring[(out_base + row) & (RING_ROWS - 1)] = v;
+        if (out_ring) out_ring[(out_base + row) & (RR - 1)] = v;
         else __stcg(&out_global[row], v);
     }
     __device__ __forceinline__ bool has_sink() const { return out_ring != nullptr || out_global != nullptr; }
@@ -128,7 +124,7 @@ struct RingEdge {
     // producer: before writing rows < row_end, the slots they reuse must have been consumed
     __device__ __forceinline__ void reserve(int row_end, int lane) const {
         if (out_cons) {
-            if (lane == 0) while (*out_cons < out_base + row_end - RING_ROWS) { }
+            if (lane == 0) while (*out_cons < out_base + row_end - RR) { }
             __syncwarp();
         }
     }
@@ -142,19 +138,18 @@ struct RingEdge {
     }
 };
 
+using RingEdge = RingEdgeT<RING_ROWS>;
+
 struct Best32 {
     int rowBest, rowJ; uint32_t rowC;       // last row so far (columns ascending, strict >)
     int colBest, colI; uint32_t colC;       // last column (rows ascending, strict >); valid in lane 31
 };
 
 // One block: columns [j_base, j_base + 32*K) of the pair (j_base may be negative: pad), all n rows.
-// DIRS: moves go to dirp[row * dstride] (this lane's 32-bit word of the row; the caller points dirp at the
-// lane's word of row 0).
-template <int K, class Edge, bool DIRS = false>
+template <int K, class Edge>
 __device__ __forceinline__ void block32(const uint32_t *xs, const int n, const uint32_t *ys, const int j_base,
                                         const bool first_block, const bool last_block, const Scoring sc,
-                                        const int4 *tab, const Edge &edge, const int lane, Best32 &best,
-                                        uint32_t *dirp = nullptr, const uint32_t dstride = 0) {
+                                        const int4 *tab, const Edge &edge, const int lane, Best32 &best) {
     const int Hinit = -sc.go;
     const int j0 = j_base + lane * K;
     int HX[K], HY[K], Gy[K];
@@ -205,19 +200,15 @@ __device__ __forceinline__ void block32(const uint32_t *xs, const int n, const u
             const bool store = (lane == 31) && edge.has_sink();
             {
                 const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
-                uint32_t mv;
-                row32<K, DIRS>(HX, HY, Gy, CX, CY, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
-                               sc.go, sc.ge, hprev, ginA, cprev, cinA, HoA, GoA, coA, mv);
-                if (DIRS) dirp[(size_t)iA * dstride] = mv;
+                row32<K>(HX, HY, Gy, CX, CY, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
+                         sc.go, sc.ge, hprev, ginA, cprev, cinA, HoA, GoA, coA);
                 if (store) edge.store(iA, make_int4(HoA, GoA, (int)coA, 0));
                 if (last_block && HoA > best.colBest) { best.colBest = HoA; best.colI = iA; best.colC = coA; }
             }
             if (iA + 1 < n) {
                 const int4 T = tab[xi2 >> 2];
-                uint32_t mv;
-                row32<K, DIRS>(HY, HX, Gy, CY, CX, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
-                               sc.go, sc.ge, hinA, ginB, cinA, cinB, HoB, GoB, coB, mv);
-                if (DIRS) dirp[(size_t)(iA + 1) * dstride] = mv;
+                row32<K>(HY, HX, Gy, CY, CX, selS, selI, (uint32_t)T.x, (uint32_t)T.y, (uint32_t)T.z, (uint32_t)T.w,
+                         sc.go, sc.ge, hinA, ginB, cinA, cinB, HoB, GoB, coB);
                 if (store) edge.store(iA + 1, make_int4(HoB, GoB, (int)coB, 0));
                 if (last_block && HoB > best.colBest) { best.colBest = HoB; best.colI = iA + 1; best.colC = coB; }
             }
@@ -331,12 +322,10 @@ pa_warp32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const
 // gedge_all: per CTA one column of n rows for the wrap-around edge plus the
 // virtual row.
 // ---------------------------------------------------------------------------
-// DIRS (pairalign -a): every block also stores its moves at dirs + dirs_off[e] (layout: see pa_warp32_dirs_kernel).
-template <int K, bool DIRS = false>
+template <int K>
 __global__ void __launch_bounds__(CTA_WARPS * 32, 1)
 pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const unsigned int *n_items,
-                unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows, pa_pair_result *out,
-                uint8_t *dirs = nullptr, const unsigned long long *dirs_off = nullptr) {
+                unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows, pa_pair_result *out) {
     __shared__ __align__(16) uint32_t xstage[XSTAGE_WORDS];
     __shared__ __align__(16) int4 rings[CTA_WARPS - 1][RING_ROWS];
     __shared__ int4 tab[8];
@@ -399,11 +388,7 @@ pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const 
                 if (w == CTA_WARPS - 1) edge.out_global = gedge;
                 else { edge.out_ring = rings[w]; edge.out_cons = &cons[w]; }
             }
-            if (DIRS)
-                block32<K, RingEdge, true>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best,
-                                           reinterpret_cast<uint32_t *>(dirs + dirs_off[e]) + p * 32 + lane, (uint32_t)P * 32u);
-            else
-                block32<K>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best);
+            block32<K>(xstage, n, ys, p * W - padL, p == 0, p == P - 1, sc, tab, edge, lane, best);
         }
         // combine: last row (lowest column wins ties), last column (from the warp that ran the last block)
         if (lane == 0) { bestRow[w] = best.rowBest; bestJ[w] = best.rowJ; bestRowC[w] = best.rowC; }
@@ -423,67 +408,17 @@ pa_cta32_kernel(const SeqStore S, const Scoring sc, const PairSource src, const 
 }
 
 // ---------------------------------------------------------------------------
-// pairalign -a.  The DP kernels below also keep the move of every cell, 2 bits
-// per column SLOT (slot = column + pad, the right-aligned layout of the DP),
-// row-major, row stride = P*32*K/4 bytes, at dirs + dirs_off[e].  A second
-// kernel then walks each pair back with one thread per pair.
-//
-// dirs_off[e] == ~0ull marks an element another kernel handles (the A/C/G/T
-// kernel skips pairs with IUPAC codes or gaps and vice versa).
+// pairalign -a.  The move-storing DP kernels (pa_dp_moves.cuh for A/C/G/T pairs, pa_general_dirs_kernel for the rest)
+// keep 2 bits per column SLOT (slot = column + pad, the right-aligned layout of the DP), row-major, row stride =
+// P*32*K/4 bytes, at dirs + dirs_off[e]: bit 0 = the move is not diagonal, bit 1 = left rather than up (only
+// meaningful with bit 0 set).  The kernel below then walks each pair back.
 // ---------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pa_warp32_dirs_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
-                      unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
-                      pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off, const uint32_t long_len) {
-    __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][2][STAGE_WORDS];
-    __shared__ int4 tabs[WARPS_PER_CTA][8];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
-    int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
-    const uint32_t vrow = bbuf_rows - 1;
-    constexpr int W = 32 * K;
-    for (;;) {
-        unsigned long long e = 0;
-        if (lane == 0) e = atomicAdd(work_counter, 1ull);
-        e = __shfl_sync(FULL_MASK, e, 0);
-        if (e >= count) break;
-        const uint32_t a = ia[e], b = ib[e];
-        const int n = (int)S.len[a], m = (int)S.len[b];
-        if (n == 0 || m == 0 || !(S.pure[a] && S.pure[b])) continue;
-        if ((uint32_t)max(n, m) > long_len) continue;          // the CTA-per-pair kernel has it (pa_cta32_kernel<K, true>)
-        __syncwarp();
-        const uint32_t *xs = stage_seq(S.p2 + S.off2[a], (uint32_t)(n + 15) >> 4, stage[wib][0], lane);
-        const uint32_t *ys = stage_seq(S.p2 + S.off2[b], (uint32_t)(m + 15) >> 4, stage[wib][1], lane);
-        build_tab32(tabs[wib], sc, fetch2(S.p2 + S.off2[b], 0), lane);
-        if (lane == 0) __stcg(&bbuf[vrow], make_int4(-sc.go, 0, 0, 0));
-        __syncwarp();
-        const int P = (m + W - 1) / W;
-        const int padL = P * W - m;
-        uint32_t *dpair = reinterpret_cast<uint32_t *>(dirs + dirs_off[e]);
-        Best32 best;
-        best.rowBest = INT_MIN; best.rowJ = INT_MAX; best.rowC = 0;
-        best.colBest = INT_MIN; best.colI = n - 1; best.colC = 0;
-        for (int p = 0; p < P; ++p) {
-            GlobalEdge edge;
-            edge.feed = p > 0 ? bbuf : bbuf + vrow;
-            edge.fmul = p > 0 ? 1 : 0;
-            edge.sink = p < P - 1 ? bbuf : nullptr;
-            block32<K, GlobalEdge, true>(xs, n, ys, p * W - padL, p == 0, p == P - 1, sc, tabs[wib], edge, lane, best,
-                                         dpair + p * 32 + lane, (uint32_t)P * 32u);
-        }
-        best.colBest = __shfl_sync(FULL_MASK, best.colBest, 31);
-        best.colI = __shfl_sync(FULL_MASK, best.colI, 31);
-        best.colC = __shfl_sync(FULL_MASK, best.colC, 31);
-        if (lane == 0) finish32(best, n, m, &out[e]);
-    }
-}
-
 // One warp per pair: the reference's walk (src/seqpair.cpp:146-178).  ops receives one byte per aligned
 // column in the REVERSE order the reference builds them in (it reverses at :183-188; the host does that):
 // 0 = x[i] over y[j], 1 = x[i] over a gap, 2 = gap over y[j].  kcols: strip width of the kernel that wrote the
-// moves of this pair (16 for A/C/G/T pairs, 8 for the general kernel).
+// moves of this pair (16 for A/C/G/T pairs, 8 for the general kernel).  The walk also counts what
+// hamming_distance(false) / similarity(false) count over the aligned strings (src/seqpair.cpp:238-274): columns
+// with a base on both sides, and those of them whose sets do not intersect -- res[e].len / res[e].dist.
 //
 // The walk is a chain of dependent loads, one row of the move store (a different cache line) per step, and the
 // store of a long pair (226 MB for 30 kb x 30 kb) is in DRAM by the time the walk starts.  So the warp works in
@@ -498,7 +433,7 @@ constexpr int WALK_WIN = 128;        // slots per row window (32 bytes)
 
 __global__ void __launch_bounds__(WALK_WARPS * 32)
 pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
-               const pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
+               pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
                uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
                const int k_pure, const int k_general) {
     __shared__ __align__(16) uint4 win[WALK_WARPS][2][WALK_EPOCH][2];
@@ -516,9 +451,12 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
             for (int q = 0; q < n; ++q) o[k++] = 1;
             for (int q = 0; q < m; ++q) o[k++] = 2;
             n_ops[e] = k;
+            res[e].dist = 0; res[e].len = 0;
         }
         return;
     }
+    const uint32_t *x4 = S.p4 + S.off4[a], *y4 = S.p4 + S.off4[b];
+    uint32_t n_cols = 0, n_diff = 0;
     const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : k_general);
     const int P = (m + W - 1) / W;
     const int padL = P * W - m;
@@ -576,7 +514,12 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
                                                                               : __ldcg(&d[(size_t)i * stride + (slot >> 2)]);
                     mv = (byte >> ((slot & 3) * 2)) & 3u;
                 }
-                if (mv == 0) { o[k++] = 0; --i; --j; }
+                if ((mv & 1u) == 0) {
+                    const uint32_t sx = fetch4(x4, i), sy = fetch4(y4, j);       // not on the chain of dependent loads
+                    n_cols += (sx != 0 && sy != 0) ? 1u : 0u;
+                    n_diff += (sx != 0 && sy != 0 && (sx & sy) == 0) ? 1u : 0u;
+                    o[k++] = 0; --i; --j;
+                }
                 else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
                 else { o[k++] = 2; --j; }
             }
@@ -585,7 +528,7 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
         park(buf ^ 1);
         __syncwarp();
     }
-    if (lane == 0) n_ops[e] = k;
+    if (lane == 0) { n_ops[e] = k; res[e].len = n_cols; res[e].dist = n_diff; }
 }
 
 }  // namespace pa

@@ -41,7 +41,8 @@ def main():
         cells = int((lens[ia].astype(np.int64) * lens[ib]).sum())
         print(json.dumps({"what": "pa_align_pairs_ops", "tag": a.tag, "pairs": len(ia), "cells": cells, "devices": a.devices,
                           "call_s": dt, "gcups_call": cells / dt / 1e9, "pairs_per_s": len(ia) / dt,
-                          "kernel_ms": t["kernel_ms"], "walk_ms": t["walk_ms"], "dp_cta_ms": t["dp_cta_ms"], "dp_fast_ms": t["dp_fast_ms"],
+                          "kernel_ms": t["kernel_ms"], "walk_ms": t["walk_ms"], "dp_cta_ms": t["dp_cta_ms"], "dp_duo_ms": t["dp_duo_ms"],
+                          "dp_general_ms": t["dp_general_ms"],
                           "gcups_dp": cells / max(t["kernel_ms"] - t["walk_ms"], 1e-9) / 1e6,
                           "launches": t["kernel_launches"], "op_bytes": int(n_ops.sum())}))
     finally:
