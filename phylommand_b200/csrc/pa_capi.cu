@@ -624,8 +624,10 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
         d.grid_moves_warp = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
         d.grid_moves_cta = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
         d.grid_fast = std::max(1, occ) * d.n_sm;
@@ -1000,13 +1002,15 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
     const int threads = WARPS_PER_CTA * 32;
     std::vector<unsigned long long> h_dirs_off, h_ops_off;
     std::vector<uint2> h_items, h_items_long;
-    const uint64_t wave_pairs = 2ull * (uint64_t)d.grid_moves_cta;       // one wave of the CTA-per-item grid
+    const uint64_t wave_items = (uint64_t)d.grid_moves_cta;              // one wave of the CTA-per-item grid
     uint64_t s0 = lo;
     while (s0 < hi) {
         // one batch: as many pairs as the move store holds
-        uint64_t e0 = s0, dbytes = 0, obytes = 0, n_long = 0;
-        uint64_t ck_e0 = s0, ck_dbytes = 0, ck_obytes = 0;      // the batch as it was after the last whole wave of long pairs
+        uint64_t e0 = s0, dbytes = 0, obytes = 0, n_long = 0, n_long_items = 0;
+        uint64_t ck_e0 = s0, ck_dbytes = 0, ck_obytes = 0;      // the batch as it was after the last whole wave of long items
         bool any_general = false;
+        bool open = false, open_long = false;                   // the last entry began a work item that may still take a partner
+        uint32_t open_a = 0;
         h_dirs_off.clear(); h_ops_off.clear();
         while (e0 < hi && e0 - s0 < (1ull << 20)) {
             const uint32_t a = ia[e0], b = ib[e0];
@@ -1026,10 +1030,17 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             h_ops_off.push_back(obytes);
             dbytes += need;
             obytes += (uint64_t)c.len[a] + c.len[b];
-            if (pure && fast && need) { if (std::max(c.len[a], c.len[b]) > LONG_LEN) ++n_long; }
-            else if (need) any_general = true;
+            if (pure && fast && need) {      // same pairing rule as the item loop below: neighbours with the same first sequence
+                const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
+                if (lng) ++n_long;
+                if (open && open_a == a && open_long == lng) open = false;
+                else { open = true; open_a = a; open_long = lng; if (lng) ++n_long_items; }
+            } else {
+                open = false;
+                if (need) any_general = true;
+            }
             ++e0;
-            if (n_long == e0 - s0 && n_long % wave_pairs == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
+            if (n_long == e0 - s0 && n_long_items % wave_items == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
         }
         const uint64_t nb = e0 - s0;
         // work items of the s16x2 kernels: neighbouring entries with the same first sequence go together
@@ -1100,11 +1111,11 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaEventRecord(d.ev[3], d.stream));
         if (!h_items_long.empty()) {
             if (prm.gap_ext == -1)
-                pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, 0, d.stream>>>(
+                pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM, d.stream>>>(
                     S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
                     d.d_res, d.d_dirs, d.d_dirs_off);
             else
-                pa_cta_duo_moves_kernel<0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, 0, d.stream>>>(
+                pa_cta_duo_moves_kernel<0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM, d.stream>>>(
                     S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
                     d.d_res, d.d_dirs, d.d_dirs_off);
             CU(cudaGetLastError());

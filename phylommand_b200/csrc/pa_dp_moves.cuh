@@ -15,6 +15,14 @@
 // P * 512 slots per row, right-aligned) -- each pair in its OWN geometry: pair 2 of an item may need fewer blocks
 // than pair 1, its words then start at the first block that holds one of its columns.
 //
+// Stores: the wavefront is skewed (lane l is on row 2(t - l) at step t), so storing a lane's word when it is made
+// would scatter every warp store over 32 rows, 4 bytes each -- 32 partial-sector writes per instruction, which L2
+// answers with a fill read and a second write-back (measured: 1.7 x the move bytes written, 0.7 x read, the kernel
+// waiting on memory at 37 % issue utilisation).  Each lane therefore delays its words in a private 8-deep ring in
+// shared memory by 7 - (lane mod 8) steps: the eight lanes that share a 32-byte sector of a row then store their
+// words of that row in the same instruction -- four full sectors per warp store, streaming (st.global.cs) so that the
+// moves do not push the edge rows out of L2.  No exchange between lanes, hence no synchronisation.
+//
 // Scores beyond int16 (pairs longer than max_len16) use the floating window of align_warp_duo: per-lane 32-bit
 // offsets, re-based by WIN_Q when the lane's right edge leaves +-WIN_T; the edge rows carry their offsets.
 //
@@ -33,8 +41,11 @@ constexpr int MOVES_CTA_WARPS = 12;      // warps per item in the CTA form: 3 pe
 #ifndef MOVES_WARP_MINB
 #define MOVES_WARP_MINB 3
 #endif
+constexpr int MOVES_DELAY = 8;            // depth of a lane's delay ring (steps): 32-byte sector / 4-byte word
 constexpr int MOVES_RING_ROWS = 128;     // rows per shared-memory edge ring (11 rings + the staged x stay below 48 KB)
 using MovesRing = RingEdgeT<MOVES_RING_ROWS>;
+constexpr size_t MOVES_CTA_SMEM = (size_t)XSTAGE_WORDS * 4 + (size_t)(MOVES_CTA_WARPS - 1) * MOVES_RING_ROWS * 16 +
+                                  (size_t)MOVES_CTA_WARPS * 2 * MOVES_DELAY * 32 * 8;
 
 template <int K, int GEC = 0>
 __device__ __forceinline__ void duo_moves_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
@@ -101,7 +112,8 @@ template <int K, class Edge, bool WIN, int GEC>
 __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n, const uint32_t *ys1, const uint32_t *ys2,
                                                 const int j_base1, const int j_base2, const bool last_block, const Scoring sc,
                                                 const int4 *tab, const Edge &edge, const int lane, BestDuo &best,
-                                                uint32_t *dirp1, const uint32_t dstride1, uint32_t *dirp2, const uint32_t dstride2) {
+                                                uint32_t *dirp1, const uint32_t dstride1, uint32_t *dirp2, const uint32_t dstride2,
+                                                uint2 *delay) {        // this warp's 2 x MOVES_DELAY x 32 delay ring
     const int B = WIN ? WIN_BIAS : sc.bias16;
     const uint32_t Bpk = pack16(B, B);
     const int Hinit = -sc.go + B;
@@ -156,14 +168,12 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
         fB = edge.load(min(2 * t + 3, n - 1));
         const uint32_t xi2 = (xw >> ((iA & 15) * 2)) & 15u;
         xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
+        uint2 mvP1 = make_uint2(0u, 0u), mvP2 = mvP1;      // moves of rows iA (x) and iA + 1 (y), pair 1 and pair 2
         if (iA >= 0 && iA < n) {
             const bool store = (lane == 31) && edge.has_sink();
             {
                 const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
-                uint32_t mv1, mv2;
-                duo_moves_row<K, GEC>(HX, HY, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hprev, ginA, HoA, GoA, mv1, mv2);
-                if (dirp1) dirp1[(size_t)iA * dstride1] = mv1;
-                if (dirp2) dirp2[(size_t)iA * dstride2] = mv2;
+                duo_moves_row<K, GEC>(HX, HY, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hprev, ginA, HoA, GoA, mvP1.x, mvP2.x);
                 if (store) edge.store(iA, make_int4((int)HoA, (int)GoA, off1, off2));
                 if (last_block) {
                     if (WIN) {
@@ -180,10 +190,7 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
             }
             if (iA + 1 < n) {
                 const int4 T = tab[xi2 >> 2];
-                uint32_t mv1, mv2;
-                duo_moves_row<K, GEC>(HY, HX, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hinA, ginB, HoB, GoB, mv1, mv2);
-                if (dirp1) dirp1[(size_t)(iA + 1) * dstride1] = mv1;
-                if (dirp2) dirp2[(size_t)(iA + 1) * dstride2] = mv2;
+                duo_moves_row<K, GEC>(HY, HX, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hinA, ginB, HoB, GoB, mvP1.y, mvP2.y);
                 if (store) edge.store(iA + 1, make_int4((int)HoB, (int)GoB, off1, off2));
                 if (last_block) {
                     if (WIN) {
@@ -214,6 +221,18 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
                     HoA = __vsub2(HoA, dPk); GoA = __vsub2(GoA, dPk); HoB = __vsub2(HoB, dPk); GoB = __vsub2(GoB, dPk);
                     off1 += d1; off2 += d2;
                 }
+            }
+        }
+        {   // delayed, sector-aligned stores of the moves (see the header): this lane's words of j7 steps ago
+            const int j7 = 7 - (lane & 7);
+            delay[(t & (MOVES_DELAY - 1)) * 32 + lane] = mvP1;
+            delay[(MOVES_DELAY + (t & (MOVES_DELAY - 1))) * 32 + lane] = mvP2;
+            const uint2 w1 = delay[((t - j7) & (MOVES_DELAY - 1)) * 32 + lane];
+            const uint2 w2 = delay[(MOVES_DELAY + ((t - j7) & (MOVES_DELAY - 1))) * 32 + lane];
+            const int iD = iA - 2 * j7;
+            if (iD >= 0 && iD < n) {
+                if (dirp1) { __stcs(&dirp1[(size_t)iD * dstride1], w1.x); if (iD + 1 < n) __stcs(&dirp1[(size_t)(iD + 1) * dstride1], w1.y); }
+                if (dirp2) { __stcs(&dirp2[(size_t)iD * dstride2], w2.x); if (iD + 1 < n) __stcs(&dirp2[(size_t)(iD + 1) * dstride2], w2.y); }
             }
         }
         if (((t - 31) & (CHUNK_STEPS - 1)) == CHUNK_STEPS - 1 && t >= 31) edge.release(min(n, 2 * (t - 31) + 2), lane);
@@ -278,6 +297,7 @@ pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia,
                          const uint32_t bbuf_rows, pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
     __shared__ int4 tabs[WARPS_PER_CTA][8];
+    __shared__ __align__(8) uint2 delays[WARPS_PER_CTA][2 * MOVES_DELAY * 32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
@@ -314,9 +334,9 @@ pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia,
             uint32_t *q1 = b1 >= 0 ? d1 + b1 * 32 + lane : nullptr;
             uint32_t *q2 = (it.two && b2 >= 0) ? d2 + b2 * 32 + lane : nullptr;
             if (win) block_duo_moves<KMOV, GlobalEdge, true, GEC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
-                                                                  edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u);
+                                                                  edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
             else block_duo_moves<KMOV, GlobalEdge, false, GEC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
-                                                               edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u);
+                                                               edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
         }
         best.colBest1 = __shfl_sync(FULL_MASK, best.colBest1, 31); best.colI1 = __shfl_sync(FULL_MASK, best.colI1, 31);
         best.colBest2 = __shfl_sync(FULL_MASK, best.colBest2, 31); best.colI2 = __shfl_sync(FULL_MASK, best.colI2, 31);
@@ -335,8 +355,11 @@ pa_cta_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, 
                         const uint32_t n_items, unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows,
                         pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off) {
     constexpr int NW = MOVES_CTA_WARPS;
-    __shared__ __align__(16) uint32_t xstage[XSTAGE_WORDS];
-    __shared__ __align__(16) int4 rings[NW - 1][MOVES_RING_ROWS];
+    // dynamic shared memory (MOVES_CTA_SMEM bytes, above the 48 KB a kernel gets statically): x, the edge rings, the delay rings
+    extern __shared__ __align__(16) unsigned char moves_smem[];
+    uint32_t *xstage = reinterpret_cast<uint32_t *>(moves_smem);
+    int4 (*rings)[MOVES_RING_ROWS] = reinterpret_cast<int4 (*)[MOVES_RING_ROWS]>(moves_smem + XSTAGE_WORDS * 4);
+    uint2 *delays = reinterpret_cast<uint2 *>(moves_smem + XSTAGE_WORDS * 4 + (NW - 1) * MOVES_RING_ROWS * 16);
     __shared__ int4 tab[8];
     __shared__ int prod[NW], cons[NW];
     __shared__ unsigned long long item_s;
@@ -397,7 +420,7 @@ pa_cta_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, 
             uint32_t *q1 = b1 >= 0 ? d1 + b1 * 32 + lane : nullptr;
             uint32_t *q2 = (it.two && b2 >= 0) ? d2 + b2 * 32 + lane : nullptr;
             block_duo_moves<KMOV, MovesRing, true, GEC>(xstage, n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tab, edge, lane,
-                                                       best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u);
+                                                       best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays + w * 2 * MOVES_DELAY * 32);
         }
         if (lane == 0) { bRow1[w] = best.rowBest1; bJ1[w] = best.rowJ1; bRow2[w] = best.rowBest2; bJ2[w] = best.rowJ2; }
         if (lane == 31 && ((P - 1) % NW) == w) { bCol1 = best.colBest1; bColI1 = best.colI1; bCol2 = best.colBest2; bColI2 = best.colI2; }

@@ -24,7 +24,7 @@ run_step() {
     py)     timeout ${T:-1500} python "$@" > "$log" 2>&1; tail -40 "$log" ;;
     sh)     timeout ${T:-1500} bash -c "$*" > "$log" 2>&1; tail -40 "$log" ;;
     ncu)    local rx=$1; shift; [ "$1" = "--" ] && shift
-            timeout ${T:-1500} ncu --set full --clock-control none --import-source on -k "regex:$rx" -c ${NCU_COUNT:-1} \
+            timeout ${T:-1500} ncu --set full --clock-control none --import-source on -k "regex:$rx" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-1} \
               -f -o gpurun_out/${TAG}_${step}_ncu "$@" > "$log" 2>&1; tail -5 "$log" ;;
     launches) [ "$1" = "--" ] && shift
             timeout ${T:-1500} ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-400} --csv \

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--length", type=int, default=30000)
     ap.add_argument("--devices", default="0")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--waves", type=int, default=0, help="pair list of exactly WAVES x 148 two-pair work items (rows of 148 pairs) instead of a triangle prefix")
     a = ap.parse_args()
     _, seqs = synth.make_long(a.seqs, 1005, length=a.length)
     enc = [synth.to_masks(s) for s in seqs]
@@ -33,6 +34,9 @@ def main():
         n = len(enc)
         ia = np.array([x for x in range(n) for y in range(x + 1, n)], dtype=np.uint32)[:a.pairs]
         ib = np.array([y for x in range(n) for y in range(x + 1, n)], dtype=np.uint32)[:a.pairs]
+        if a.waves:
+            ia = np.repeat(np.arange(2 * a.waves, dtype=np.uint32), 148)
+            ib = (ia + 1 + np.tile(np.arange(148, dtype=np.uint32), 2 * a.waves)) % n
         capi.align_pairs_ops(ia[:8], ib[:8], lens)                 # warm-up: allocations, module load
         t0 = time.perf_counter()
         ops, off, n_ops, res = capi.align_pairs_ops(ia, ib, lens)
