@@ -12,7 +12,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpairalign_b200.so"
+import os
+
+#: PAIRALIGN_B200_LIB points the binding at another build of the same module (kernel A/B experiments, tools/gpu_run.sh)
+LIB_PATH = Path(os.environ.get("PAIRALIGN_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libpairalign_b200.so")
 
 PA_OK, PA_EINVAL, PA_ENODEVICE, PA_ECUDA, PA_ENOMEM, PA_ERANGE = 0, -1, -2, -3, -4, -5
 

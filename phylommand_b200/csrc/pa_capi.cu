@@ -401,8 +401,8 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
         CU(cudaGetLastError());
         d.launches += 1;
         if (amb) {   // the items with an ambiguous sequence: same work items, 4-bit-set variant (its own work counter)
-            if (p.gap_ext == -1)
-                pa_warp_sets_kernel<-1><<<d.grid_sets, threads, 0, d.stream>>>(
+            if (p.gap_ext == -1 && p.match - p.mismatch == 12)
+                pa_warp_sets_kernel<-1, 12><<<d.grid_sets, threads, 0, d.stream>>>(
                     S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
             else
                 pa_warp_sets_kernel<0><<<d.grid_sets, threads, 0, d.stream>>>(
@@ -619,7 +619,7 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
         d.grid_duo_auto = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1>, WARPS_PER_CTA * 32, 0);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1, 12>, WARPS_PER_CTA * 32, 0);
         d.grid_sets = std::max(1, std::min(occ, occ_c)) * d.n_sm;
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);

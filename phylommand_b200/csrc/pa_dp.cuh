@@ -30,6 +30,11 @@
 // cnt packs (columns << 16 | mismatches).
 #pragma once
 
+#ifndef PA_DUO_ADD_VARIANT
+#define PA_DUO_ADD_VARIANT 0    // measured on B200 (profiles/r02_add_placement.txt): 0 plain adds 2534 GCUPS, 1 H+GO as IMAD with a register
+#endif                          // multiplier 2461, 2 all three adds so 2394, 3 counter adds as IMAD with an immediate multiplier 2462
+
+
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <limits.h>
@@ -53,7 +58,10 @@ struct SeqStore {
     uint32_t n_seq;
 };
 
-struct Scoring { int match, mismatch, go, ge; int bias16 = 0; int one = 1; };   // bias16: see duo_row (s16x2 kernels only); one: fma_add
+// bias16: see duo_row (s16x2 kernels only).  one, one2: both 1 -- multipliers that turn an add into an IMAD the compiler cannot
+// move to the ALU pipe; two of them so that ptxas can keep one in a uniform register (IMAD R, R, UR, R) while the other
+// sits in a vector register next to a uniform addend (IMAD R, R, R, UR): either way two vector-register operands.
+struct Scoring { int match, mismatch, go, ge; int bias16 = 0; int one = 1; int one2 = 1; };
 
 struct PairSource {
     uint64_t first;          // triangle mode: global index of element 0
@@ -382,7 +390,7 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
                                         const uint32_t (&C2s)[K], uint32_t (&C2d)[K],
                                         const uint32_t (&selS)[K], const uint32_t (&selI1)[K], const uint32_t (&selI2)[K],
                                         const uint32_t Rlo, const uint32_t Rhi, const uint32_t Mlo, const uint32_t Mhi,
-                                        const uint32_t GOc, const uint32_t GEpk,
+                                        const uint32_t GOc, const uint32_t GEpk, const uint32_t one, const uint32_t one2,
                                         uint32_t hdiag, uint32_t Gl, uint32_t cd1, uint32_t cd2, uint32_t cl1, uint32_t cl2,
                                         uint32_t &Hout, uint32_t &Gxout, uint32_t &c1out, uint32_t &c2out) {
     const uint32_t GE2 = GEC ? ((uint32_t)GEC & 0xffffu) * 0x10001u : GEpk;
@@ -395,13 +403,24 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
         const uint32_t Gu = Gy[k];
         const uint32_t cu1 = C1s[k], cu2 = C2s[k];
         const uint32_t h = __vadd2(__vimax3_s16x2(Hdg, Gu, Gl), s);
-        const uint32_t o = Hdg + GOc;                                // IMAD.IADD: both halves + GO (see above)
+#if PA_DUO_ADD_VARIANT == 0
+        const uint32_t o = Hdg + GOc;
+#else
+        const uint32_t o = Hdg * one + GOc;                          // IMAD: both halves + GO (see above); one = 1, opaque to ptxas,
+                                                                     // which otherwise moves this add to the ALU pipe when it likes
+#endif
         const uint32_t gy = __viaddmax_s16x2(Gu, GE2, o);
         const uint32_t gx = __viaddmax_s16x2(Gl, GE2, o);
         bool pUhi, pUlo, pDhi, pDlo;
         const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);         // gy >= gx
         (void)vibmax_s16x2(h, g, pDhi, pDlo);                        // h >= max(gy, gx)
+#if PA_DUO_ADD_VARIANT == 2
+        const uint32_t cdi1 = cd1 * one2 + inc1, cdi2 = cd2 * one2 + inc2;
+#elif PA_DUO_ADD_VARIANT == 3
+        const uint32_t cdi1 = inc1 * 3u + cd1, cdi2 = inc2 * 3u + cd2;       // counters hold 3 x (columns, mismatches): IMAD with an immediate
+#else
         const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
+#endif
         const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
         const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
         Hdg = Hs[k]; cd1 = cu1; cd2 = cu2;
@@ -438,6 +457,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
     const int Hinit = -sc.go + B;
     const uint32_t HinitPk = pack16(Hinit, Hinit);
     const uint32_t GOc = sc.go ? pack16(sc.go, sc.go - 1) : 0u, GEpk = pack16(sc.ge, sc.ge);
+    const uint32_t one = (uint32_t)sc.one, one2 = (uint32_t)sc.one2;
 
     int rowBest1 = INT_MIN, rowJ1 = 0, rowBest2 = INT_MIN, rowJ2 = 0;
     uint32_t rowC1 = 0, rowC2 = 0;
@@ -534,7 +554,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                 {   // even row iA: previous row in X, result in Y
                     const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
                     duo_row<K, GEC>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
-                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
+                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk, one, one2,
                                hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
                     if (store) {
                         if (WIN) {
@@ -558,7 +578,7 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
                 if (iA + 1 < n) {   // odd row iA+1: previous row in Y, result in X
                     const int4 T = tab[xi2 >> 2];
                     duo_row<K, GEC>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, selS, selI1, selI2, (uint32_t)T.x, (uint32_t)T.y,
-                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk,
+                               (uint32_t)T.z, (uint32_t)T.w, GOc, GEpk, one, one2,
                                hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
                     if (store) {
                         if (WIN) {

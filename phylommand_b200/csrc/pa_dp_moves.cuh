@@ -5,9 +5,9 @@
 // What a cell costs here: the score PRMT, VIMNMX3, VIADD.16x2, two VIADDMNMX and the two predicate-producing
 // VIMNMX.S16x2 on the ALU pipe (7), H + GO and FOUR PREDICATED IMADs on the FMA pipe: bit 0 of a cell's move is
 // "not diagonal", bit 1 "left rather than up", and `@!p IMAD mv, mv, one, imm` adds the bit where the predicate says
-// so (one = a register holding 1, imm = the bit at this column's position).  No counters, no increment tables, no
-// selects: 19 dispatch cycles for two cells where the statistics kernel spends 25, and half the hand-over per row
-// (H and Gx only).  The statistics (compared / differing columns) are counted by the walk.
+// so (one = a register holding 1, imm = the bit at this column's position).
+// No counters, no increment tables, no selects, and half the hand-over per row (H and Gx only).  The statistics
+// (compared / differing columns) are counted by the walk.
 //
 // Work item: two entries (x, y1), (x, y2) of the caller's pair list that share their first sequence (the order
 // pairalign visits the triangle in), or one entry alone.  Strip width 16: one 32-bit word of moves per lane, row and
@@ -67,7 +67,9 @@ __device__ __forceinline__ void duo_moves_row(const uint32_t (&Hs)[K], uint32_t 
         bool pUhi, pUlo, pDhi, pDlo;
         const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);      // gy >= gx
         (void)vibmax_s16x2(h, g, pDhi, pDlo);                     // h >= max(gy, gx)
-        m1 = pDlo ? m1 : m1 * one + (1u << (2 * k));              // @!p IMAD mv, mv, one, imm
+        // @!p IMAD mv, mv, one, imm.  Measured alternatives (profiles/r02_add_placement.txt): written as one * imm + mv, ptxas
+        // strength-reduces the power of two and selects / adds on the ALU pipe instead: 34 -> 60 ms on the 1.5 kb set
+        m1 = pDlo ? m1 : m1 * one + (1u << (2 * k));
         m1 = pUlo ? m1 : m1 * one + (2u << (2 * k));
         m2 = pDhi ? m2 : m2 * one + (1u << (2 * k));
         m2 = pUhi ? m2 : m2 * one + (2u << (2 * k));

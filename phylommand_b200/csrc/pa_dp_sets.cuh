@@ -40,15 +40,15 @@ __device__ __forceinline__ uint32_t bitsel(const uint32_t a, const uint32_t b, c
     asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
     return d;
 }
-// a + b on the FMA pipe: `one` is a kernel parameter that holds 1, so the compiler has to issue IMAD
-__device__ __forceinline__ uint32_t fma_add(const uint32_t a, const uint32_t b, const uint32_t one) { return a * one + b; }
 
-template <int K, int GEC = 0>
+// DC != 0: match - mismatch is the compile-time constant DC (12 for pairalign's scoring) and multiplies the hit bits as an
+// immediate; an IMAD with a register multiplier costs several times more (profiles/r02_add_placement.txt).
+template <int K, int GEC = 0, int DC = 0>
 __device__ __forceinline__ void sets_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
                                          const uint32_t (&C1s)[K], uint32_t (&C1d)[K],
                                          const uint32_t (&C2s)[K], uint32_t (&C2d)[K],
                                          const uint32_t (&HV)[K], const uint32_t (&XAc)[K], const uint32_t (&LC)[K],
-                                         const uint32_t rowset, const uint32_t Dmul, const uint32_t one, const uint32_t GOc, const uint32_t GEpk,
+                                         const uint32_t rowset, const uint32_t Dmul, const uint32_t GOc, const uint32_t GEpk,
                                          uint32_t hdiag, uint32_t Gl, uint32_t cd1, uint32_t cd2, uint32_t cl1, uint32_t cl2,
                                          uint32_t &Hout, uint32_t &Gxout, uint32_t &c1out, uint32_t &c2out) {
     const uint32_t GE2 = GEC ? ((uint32_t)GEC & 0xffffu) * 0x10001u : GEpk;
@@ -60,18 +60,18 @@ __device__ __forceinline__ void sets_row(const uint32_t (&Hs)[K], uint32_t (&Hd)
         const uint32_t inc2 = bitsel(t2, LC[k], 0x00000001u);             // hit << 16 | column flag
         const uint32_t Gu = Gy[k];
         const uint32_t cu1 = C1s[k], cu2 = C2s[k];
-        const uint32_t m3x = fma_add(__vimax3_s16x2(Hdg, Gu, Gl), XAc[k], one);   // 32-bit add, exact per half (pre-borrowed)
+        const uint32_t m3x = __vimax3_s16x2(Hdg, Gu, Gl) + XAc[k];        // 32-bit add, exact per half (pre-borrowed)
         // + (match - mismatch) where the sets intersect.  A packed add on purpose: when h is the result of a 32-bit IMAD,
         // ptxas leaves a dead PRMT per cell behind the predicate-producing VIMNMX.S16x2 below (same ALU-pipe cost, one
         // FMA-pipe instruction more)
-        const uint32_t h = __vadd2(t2 * Dmul, m3x);
-        const uint32_t o = fma_add(Hdg, GOc, one);
+        const uint32_t h = __vadd2(DC ? t2 * (uint32_t)DC : t2 * Dmul, m3x);
+        const uint32_t o = Hdg + GOc;
         const uint32_t gy = __viaddmax_s16x2(Gu, GE2, o);
         const uint32_t gx = __viaddmax_s16x2(Gl, GE2, o);
         bool pUhi, pUlo, pDhi, pDlo;
         const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);
         (void)vibmax_s16x2(h, g, pDhi, pDlo);                             // h >= max(gy, gx)
-        const uint32_t cdi1 = fma_add(cd1, inc1, one), cdi2 = fma_add(cd2, inc2, one);
+        const uint32_t cdi1 = cd1 + inc1, cdi2 = cd2 + inc2;
         const uint32_t c1 = pDlo ? cdi1 : (pUlo ? cu1 : cl1);
         const uint32_t c2 = pDhi ? cdi2 : (pUhi ? cu2 : cl2);
         Hdg = Hs[k]; cd1 = cu1; cd2 = cu2;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void sets_row(const uint32_t (&Hs)[K], uint32_t (&Hd)
 }
 
 // xs / ys1 / ys2: 4-bit sets, 8 per word.  Everything else as align_warp_duo.
-template <int K, bool WIN = false, int GEC = 0>
+template <int K, bool WIN = false, int GEC = 0, int DC = 0>
 __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n, const uint32_t *ys1, const int m1,
                                                 const uint32_t *ys2, const int m2, const Scoring sc, int4 *bbuf,
                                                 const uint32_t vrow, pa_pair_result *res1, pa_pair_result *res2, const int lane) {
@@ -96,7 +96,6 @@ __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n,
     const uint32_t HinitPk = pack16(Hinit, Hinit);
     const uint32_t GOc = sc.go ? pack16(sc.go, sc.go - 1) : 0u, GEpk = pack16(sc.ge, sc.ge);
     const uint32_t Dmul = (uint32_t)(sc.match - sc.mismatch);            // >= 0 (host-checked)
-    const uint32_t one = (uint32_t)sc.one;                               // 1, opaque to the compiler (fma_add)
     const bool dM = sc.match >= 0, dX = sc.mismatch >= 0;                // first row: the move is D iff the score is >= 0
 
     int rowBest1 = INT_MIN, rowJ1 = 0, rowBest2 = INT_MIN, rowJ2 = 0;
@@ -185,7 +184,7 @@ __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n,
                     }
                     HoA = HY[K - 1]; GoA = Bpk; c1oA = C1Y[K - 1]; c2oA = C2Y[K - 1];
                 } else {
-                    sets_row<K, GEC>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, HV, XAc, LC, mA, Dmul, one, GOc, GEpk,
+                    sets_row<K, GEC, DC>(HX, HY, Gy, C1X, C1Y, C2X, C2Y, HV, XAc, LC, mA, Dmul, GOc, GEpk,
                                      hprev, ginA, c1prev, c2prev, c1inA, c2inA, HoA, GoA, c1oA, c2oA);
                 }
                 if (store) {
@@ -207,7 +206,7 @@ __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n,
                     }
                 }
                 if (iA + 1 < n) {
-                    sets_row<K, GEC>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, HV, XAc, LC, mB, Dmul, one, GOc, GEpk,
+                    sets_row<K, GEC, DC>(HY, HX, Gy, C1Y, C1X, C2Y, C2X, HV, XAc, LC, mB, Dmul, GOc, GEpk,
                                      hinA, ginB, c1inA, c2inA, c1inB, c2inB, HoB, GoB, c1oB, c2oB);
                     if (store) {
                         if (WIN) {
@@ -300,7 +299,8 @@ __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n,
 // pa_warp_duo_kernel<0>, which leaves exactly these to this launch (amb_launch).  setok[s]: sequence s has no gap
 // character.  Items this kernel cannot take (a gap character, too long without the window) were deferred by the
 // plain launch.
-template <int GEC = 0>
+// GEC / DC: compile-time gap extension / match - mismatch (the host launches <-1, 12> for pairalign's scoring), 0 = run time.
+template <int GEC = 0, int DC = 0>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
                     const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
@@ -349,8 +349,8 @@ pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, co
         __syncwarp();
         pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
         const bool too_long = (uint32_t)n > max_len16 || (uint32_t)my1 > max_len16 || (uint32_t)my2 > max_len16;
-        if (too_long) align_warp_sets<12, true, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, r1, r2, lane);
-        else align_warp_sets<12, false, GEC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, r1, r2, lane);
+        if (too_long) align_warp_sets<12, true, GEC, DC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, r1, r2, lane);
+        else align_warp_sets<12, false, GEC, DC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, r1, r2, lane);
     }
 }
 
