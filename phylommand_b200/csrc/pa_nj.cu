@@ -52,6 +52,25 @@ constexpr int NJ_ROW_PAD = 256;               // allocated rows are a multiple o
 
 struct JoinRec { uint32_t left, right; float length, s_i, s_j; int r, pi, pj; };
 
+// Programmatic dependent launch: the three kernels of a join are launched with programmaticStreamSerialization, let their
+// successor's CTAs become resident at once (launch_dependents) and only then wait for their predecessor's memory
+// (griddepcontrol.wait).  The launch latency of kernel k+1 then overlaps kernel k instead of following it -- below a
+// few thousand taxa the joins are launch-bound, not bandwidth-bound.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ __forceinline__ unsigned int ordered_bits(float v) {
     v = v + 0.0f;                              // -0 -> +0: they compare equal in the reference
 #ifdef __CUDA_ARCH__
@@ -102,6 +121,7 @@ __global__ void nj_init(unsigned long long *key, const int n_keys, uint32_t *nod
 __global__ void __launch_bounds__(NJ_THREADS) nj_argmin(const float *__restrict__ M, const int ld, const int first, const int P,
                                                         const int r, const float *__restrict__ S, const uint8_t *__restrict__ alive,
                                                         unsigned long long *key, unsigned int *ticket) {
+    pdl_enter();
     const float fr2 = (float)(r - 2);
     float bv = NJ_START;
     unsigned int brank = 0xffffffffu;
@@ -193,6 +213,7 @@ constexpr int NJ_STAGES = 6;                   // 8 KB tiles: 5 of them (40 KB) 
 __global__ void __launch_bounds__(256) nj_update(float *M, const int ld, const int first, const int P, const int r,
                                                  const float *__restrict__ S, uint32_t *node, uint8_t *alive,
                                                  const unsigned long long *key, JoinRec *rec, const uint32_t new_id) {
+    pdl_enter();
     const unsigned int rank = (unsigned int)*key;
     const int i = (int)(rank >> 16), jp = (int)(rank & 0xffffu), nw = first - 1;
     const size_t ldz = (size_t)ld;
@@ -231,6 +252,7 @@ __global__ void __launch_bounds__(32) nj_sums(const SumArgs g, const __grid_cons
     constexpr int W = NJ_W, TR = NJ_TR;
     extern __shared__ __align__(128) float tile[];         // [NJ_STAGES][TR][W]
     __shared__ __align__(8) uint64_t full[NJ_STAGES];
+    pdl_enter();
     const int P = g.P, lane = threadIdx.x;
     const int b0 = (g.lo / W) * W + blockIdx.x * W;
     const int a_start = (g.lo / TR) * TR;
@@ -285,7 +307,7 @@ bool make_tile_map(float *base, int rows, int ld, CUtensorMap *out) {
 void launch_sums(cudaStream_t st, const SumArgs &a, const CUtensorMap &map) {
     const int span = a.P - (a.lo / NJ_W) * NJ_W;
     const int blocks = (span + NJ_W - 1) / NJ_W;
-    nj_sums<<<blocks, 32, sums_smem(), st>>>(a, map);
+    launch_pdl(nj_sums, dim3(blocks), dim3(32), sums_smem(), st, a, map);
 }
 
 // ---- compaction: live slots of [first, P) -> slots [k2, k2 + r) of the other buffer, order kept ------------------
@@ -415,10 +437,10 @@ int pa_nj_build(const float *dist, uint32_t n, pa_nj_join *joins, uint32_t *root
         for (int round = 0; r > 2 && e == cudaSuccess; ++round) {
             if (first == 0) compact(epoch_len(r));
             const int span = P - first;
-            nj_argmin<<<span - 1 < 148 * 8 ? span - 1 : 148 * 8, NJ_THREADS, 0, st>>>(M[mcur], ld, first, P, r, S[scur], alive[ncur],
-                                                                                     key + round, ticket);
-            nj_update<<<(span + 255) / 256, 256, 0, st>>>(M[mcur], ld, first, P, r, S[scur], node[ncur], alive[ncur], key + round,
-                                                          rec + round, next_id++);
+            launch_pdl(nj_argmin, dim3(span - 1 < 148 * 8 ? span - 1 : 148 * 8), dim3(NJ_THREADS), 0, st, (const float *)M[mcur], ld, first, P, r,
+                       (const float *)S[scur], (const uint8_t *)alive[ncur], key + round, ticket);
+            launch_pdl(nj_update, dim3((span + 255) / 256), dim3(256), 0, st, M[mcur], ld, first, P, r, (const float *)S[scur], node[ncur],
+                       alive[ncur], (const unsigned long long *)(key + round), rec + round, next_id++);
             --first; --r;
             a.M = M[mcur]; a.P = P; a.lo = first; a.S2 = S[scur ^ 1]; a.alive = alive[ncur];
             launch_sums(st, a, maps[mcur]);
