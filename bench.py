@@ -542,6 +542,8 @@ def main() -> None:
             line["roofline"] = rf
         if shapes:
             line["shapes"] = shapes
+            if "c3" in shapes and world > 1:      # the north_star target under its own name: the full 10,000 x 1.5 kb set, fixed, cut over N GPUs
+                line["c3_strong"] = shapes["c3"]
         if cli_equal is not None:
             line["cli_multi_device_md5_equal"] = cli_equal
         if not args.no_cpu_baseline:
