@@ -56,8 +56,10 @@ KERNELS = {
     "dp_duo_ms": "pa_warp_duo_kernel (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per "
                  "lane per work item; floating 16-bit window for pairs beyond int16; AMB variant for sparse IUPAC codes)",
     "dp_fast_ms": "pa_warp32_kernel<16> (int32, one pair per warp)",
-    "dp_cta_ms": "pa_cta32_kernel<16> (int32, one pair per CTA, shared-memory ring edges)",
+    "dp_cta_ms": "pa_cta_duo_moves_kernel (s16x2 with stored moves, one two-pair item per CTA, shared-memory ring edges; statistics "
+                 "by the walk) or pa_cta32_kernel<16> (int32, one pair per CTA) for long pairs mixed with short ones",
     "dp_general_ms": "pa_warp_dp_kernel<8,true> (int32 with wrap-around, 4-bit IUPAC sets)",
+    "walk_ms": "pa_walk_kernel (statistics of few long pairs: walk over the stored moves of pa_cta_duo_moves_kernel)",
 }
 #: ncu --set full summaries under profiles/ that belong to a workload's dominant kernel (traffic and pipe figures are
 #: only reported when the file for THIS workload exists)
@@ -356,7 +358,7 @@ def main() -> None:
         my_cells = capi.count_cells(first, count)
         total_cells = capi.count_cells(0, total_pairs)
         d_out = torch.empty(max(count, 1) * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        h_out = np.empty(count, dtype=capi.RESULT_DTYPE)
+        h_out = np.zeros(count, dtype=capi.RESULT_DTYPE)      # touched: first-touch page faults are not part of a step
         parts = {"upload_ms": 0.0, "align_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "calls": 0}
         buckets = {k: 0.0 for k in KERNELS}
 

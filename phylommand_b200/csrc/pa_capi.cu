@@ -167,7 +167,7 @@ struct Context {
     bool force_cta = false;            // PAIRALIGN_FORCE_CTA=1: every long pair takes a CTA regardless of how many there are
     uint64_t est_long_pairs = 0;       // pairs of the whole triangle with a sequence longer than LONG_LEN
     bool no_cta = false;               // PAIRALIGN_NO_CTA=1: long pairs stay on the one-pair-per-warp kernel (comparison)
-    uint32_t max_len = 0;
+    uint32_t max_len = 0, min_len = 0;
     pa_timing timing = {};
 };
 
@@ -595,7 +595,11 @@ int pa_init(const int *devices, int n_dev) {
         d.n_sm = n_sm;
         c->dev.push_back(d);
     }
-    for (auto &d : c->dev) {
+    // Streams, events, scratch and the occupancy queries (which make the driver load every kernel of the module for that
+    // device) take a few hundred milliseconds per device: every device sets itself up on its own host thread.
+    std::vector<cudaError_t> setup_err(c->dev.size(), cudaSuccess);
+    auto setup = [&](size_t k) {
+        Device &d = c->dev[k];
         cudaSetDevice(d.id);
         cudaError_t e2 = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
@@ -638,11 +642,21 @@ int pa_init(const int *devices, int n_dev) {
         if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
         d.grid_stats = std::max(1, occ) * d.n_sm;
         d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, d.grid_moves_warp), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
-        if (e2 != cudaSuccess) {
-            std::string msg = cudaGetErrorString(e2);
+        setup_err[k] = e2;
+    };
+    if (c->dev.size() == 1) setup(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < c->dev.size(); ++k) th.emplace_back(setup, k);
+        for (auto &t : th) t.join();
+    }
+    for (size_t k = 0; k < c->dev.size(); ++k) {
+        if (setup_err[k] != cudaSuccess) {
+            std::string msg = cudaGetErrorString(setup_err[k]);
+            const int bad = c->dev[k].id;
             for (auto &dd : c->dev) free_device(dd);
             delete c;
-            return fail(PA_ECUDA, "device %d setup failed: %s", d.id, msg.c_str());
+            return fail(PA_ECUDA, "device %d setup failed: %s", bad, msg.c_str());
         }
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
@@ -820,6 +834,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.host_pure = pure;
     c.len = len;
     c.max_len = max_len;
+    c.min_len = n_seq ? *std::min_element(len.begin(), len.end()) : 0;
     c.all_pure = all_pure;
     c.all_fast = all_fast;
     c.any_sparse = any_sparse;
@@ -890,6 +905,21 @@ int pa_partition_by_length(const uint32_t *lengths, uint32_t n_seq, uint64_t fir
     return PA_OK;
 }
 
+static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t *ia, const uint32_t *ib, uint64_t lo, uint64_t hi,
+                     uint8_t *ops, const uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res, double *kernel_ms,
+                     pa_pair_result *d_res_out);
+
+// A triangle range of LONG A/C/G/T pairs that is too small to fill the one-item-per-warp statistics kernel (config 5 cut
+// over 4 or 8 GPUs: a few hundred 30 kb x 30 kb items per device, each 0.8 s of one warp) runs a CTA per item instead:
+// the move-storing s16x2 kernel of pairalign -a (2.35 TCUPS) and the walk, which counts the statistics; no op strings.
+static bool few_long_items(const Context &c, const pa_params &p, uint64_t count_per_device, const Device &d) {
+    if (c.no_cta || c.force_32bit || p.aligned || !c.all_pure || c.min_len <= LONG_LEN || !fast_params_ok(p)) return false;
+    const long long win_spread = 17ll * (std::llabs((long long)p.match) + std::llabs((long long)p.mismatch) +
+                                         std::llabs((long long)p.gap_open) + std::llabs((long long)p.gap_ext));
+    if (p.gap_ext < -1024 || win_spread > 3500 || max_len16(p) < 16) return false;
+    return c.force_cta || count_per_device / 2 < 6ull * (uint64_t)d.grid_duo_auto * WARPS_PER_CTA;
+}
+
 static int align_impl(const pa_params *params, uint64_t first, uint64_t count, const uint32_t *ia, const uint32_t *ib,
                       pa_pair_result *out, pa_pair_result *d_resident) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -919,9 +949,22 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     }
     std::vector<int> rcs(nd, PA_OK);
     std::vector<std::string> errs(nd);
+    const bool via_moves = !ia && count && few_long_items(c, *params, (count + nd - 1) / nd, c.dev[0]);
+    std::vector<double> kms(2 * nd, 0.0);
     auto work = [&](size_t p) {
         const uint64_t lo = bounds[p], n = bounds[p + 1] - bounds[p];
-        if (!ia) rcs[p] = run_range(c, c.dev[p], *params, lo, n, nullptr, nullptr, out ? out + (lo - first) : nullptr, d_resident);
+        if (via_moves) {
+            Device &d = c.dev[p];
+            d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
+            d.launches = 0;
+            std::vector<uint32_t> la((size_t)n), lb((size_t)n);
+            uint32_t a = 0, b = 0;
+            if (n) tri_pair(lo, c.n_seq, a, b);
+            for (uint64_t k = 0; k < n; ++k) { la[(size_t)k] = a; lb[(size_t)k] = b; if (++b == c.n_seq) { ++a; b = a + 1; } }
+            rcs[p] = ops_range(c, d, *params, la.data(), lb.data(), 0, n, nullptr, nullptr, nullptr, out ? out + (lo - first) : nullptr,
+                               &kms[2 * p], d_resident);
+        }
+        else if (!ia) rcs[p] = run_range(c, c.dev[p], *params, lo, n, nullptr, nullptr, out ? out + (lo - first) : nullptr, d_resident);
         else rcs[p] = run_range(c, c.dev[p], *params, 0, n, ia + lo, ib + lo, out + lo, nullptr);
         if (rcs[p]) errs[p] = g_err;
     };
@@ -937,7 +980,8 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
         const Device &d = c.dev[p];
-        tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.cta_ms + d.gen_ms);
+        tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.cta_ms + d.gen_ms + kms[2 * p + 1]);
+        tm.walk_ms = std::max(tm.walk_ms, kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
         tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);
         tm.dp_fast_ms = std::max(tm.dp_fast_ms, d.fast_ms);
@@ -982,8 +1026,11 @@ static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool pure, bool fast) {
 // first sequence per work item; pairs longer than LONG_LEN take a CTA per item when a batch holds too few of them to
 // fill a warp-per-item grid -- which the size of their move stores (226 MB for 30 kb x 30 kb) all but guarantees.
 // Everything else (IUPAC codes, gap characters, scoring outside the byte tables) runs on the general int32 kernel.
+// ops == nullptr: statistics only -- no op strings are made or copied, the records (score and end cell from the DP,
+// compared / differing columns from the walk) go to res (host, indexed like ia) and / or d_res_out (device, element lo first).
 static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t *ia, const uint32_t *ib, uint64_t lo, uint64_t hi,
-                     uint8_t *ops, const uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res, double *kernel_ms) {
+                     uint8_t *ops, const uint64_t *op_offsets, uint32_t *n_ops, pa_pair_result *res, double *kernel_ms,
+                     pa_pair_result *d_res_out) {
     if (lo >= hi) return PA_OK;
     CU(cudaSetDevice(d.id));
     int bias16 = 0;
@@ -1029,7 +1076,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             h_dirs_off.push_back(dbytes);
             h_ops_off.push_back(obytes);
             dbytes += need;
-            obytes += (uint64_t)c.len[a] + c.len[b];
+            if (ops) obytes += (uint64_t)c.len[a] + c.len[b];
             if (pure && fast && need) {      // same pairing rule as the item loop below: neighbours with the same first sequence
                 const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
                 if (lng) ++n_long;
@@ -1129,14 +1176,17 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             d.launches += 1;
         }
         CU(cudaEventRecord(d.ev[1], d.stream));
-        pa_walk_kernel<<<(unsigned)((nb + WALK_WARPS - 1) / WALK_WARPS), WALK_WARPS * 32, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off, d.d_ops,
-                                                                        d.d_ops_off, d.d_nops, KMOV, KGEN);
+        pa_walk_kernel<<<(unsigned)((nb + WALK_WARPS - 1) / WALK_WARPS), WALK_WARPS * 32, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off,
+                                                                        ops ? d.d_ops : nullptr, d.d_ops_off, d.d_nops, KMOV, KGEN);
         CU(cudaGetLastError());
         d.launches += 1;
         CU(cudaEventRecord(d.ev[2], d.stream));
-        CU(cudaMemcpyAsync(ops + op_offsets[s0], d.d_ops, obytes, cudaMemcpyDeviceToHost, d.stream));
-        CU(cudaMemcpyAsync(n_ops + s0, d.d_nops, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (ops) {
+            CU(cudaMemcpyAsync(ops + op_offsets[s0], d.d_ops, obytes, cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaMemcpyAsync(n_ops + s0, d.d_nops, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+        }
         if (res) CU(cudaMemcpyAsync(res + s0, d.d_res, nb * sizeof(pa_pair_result), cudaMemcpyDeviceToHost, d.stream));
+        if (d_res_out) CU(cudaMemcpyAsync(d_res_out + (s0 - lo), d.d_res, nb * sizeof(pa_pair_result), cudaMemcpyDeviceToDevice, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         float dp_ms = 0, walk_ms = 0, warp_ms = 0, cta_ms = 0;
         CU(cudaEventElapsedTime(&dp_ms, d.ev[0], d.ev[1]));
@@ -1144,9 +1194,11 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaEventElapsedTime(&warp_ms, d.ev[0], d.ev[3]));
         CU(cudaEventElapsedTime(&cta_ms, d.ev[3], d.ev[4]));
         kernel_ms[0] += dp_ms; kernel_ms[1] += walk_ms;
-        d.duo_ms += warp_ms; d.cta_ms += cta_ms; d.gen_ms += dp_ms - warp_ms - cta_ms;
+        if (!h_items.empty()) d.duo_ms += warp_ms;
+        if (!h_items_long.empty()) d.cta_ms += cta_ms;
+        if (any_general) d.gen_ms += dp_ms - warp_ms - cta_ms;
         // the walk wrote each op string backwards (the reference reverses at src/seqpair.cpp:183-188)
-        for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);
+        if (ops) for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);
         s0 = e0;
     }
     return PA_OK;
@@ -1193,7 +1245,7 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     std::vector<double> kms(2 * nd, 0.0);
     for (auto &d : c.dev) { d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
     auto work = [&](size_t p) {
-        rcs[p] = ops_range(c, c.dev[p], *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p]);
+        rcs[p] = ops_range(c, c.dev[p], *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p], nullptr);
         if (rcs[p]) errs[p] = g_err;
     };
     if (nd == 1) work(0);

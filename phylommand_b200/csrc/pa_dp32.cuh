@@ -444,13 +444,17 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
     if (e >= count) return;
     const uint32_t a = ia[e], b = ib[e];
     const int n = (int)S.len[a], m = (int)S.len[b];
-    uint8_t *o = ops + ops_off[e];
+    // ops == nullptr: statistics only (the caller wants res[e].len / res[e].dist, not the op string)
+    const bool emit = ops != nullptr;
+    uint8_t *o = emit ? ops + ops_off[e] : nullptr;
     uint32_t k = 0;
     if (n == 0 || m == 0) {       // nothing to align (undefined in the reference): the other sequence against gaps
         if (lane == 0) {
-            for (int q = 0; q < n; ++q) o[k++] = 1;
-            for (int q = 0; q < m; ++q) o[k++] = 2;
-            n_ops[e] = k;
+            if (emit) {
+                for (int q = 0; q < n; ++q) o[k++] = 1;
+                for (int q = 0; q < m; ++q) o[k++] = 2;
+                n_ops[e] = k;
+            }
             res[e].dist = 0; res[e].len = 0;
         }
         return;
@@ -493,8 +497,10 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
     park(0);
     __syncwarp();
     if (lane == 0) {
-        if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
-        else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
+        if (emit) {
+            if (i < n - 1) { for (int pos = n - 1; pos > i; --pos) o[k++] = 1; }
+            else if (j < m - 1) { for (int pos = m - 1; pos > j; --pos) o[k++] = 2; }
+        }
     }
     for (int buf = 0;; buf ^= 1) {
         i = __shfl_sync(FULL_MASK, i, 0);
@@ -518,17 +524,18 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
                     const uint32_t sx = fetch4(x4, i), sy = fetch4(y4, j);       // not on the chain of dependent loads
                     n_cols += (sx != 0 && sy != 0) ? 1u : 0u;
                     n_diff += (sx != 0 && sy != 0 && (sx & sy) == 0) ? 1u : 0u;
-                    o[k++] = 0; --i; --j;
+                    if (emit) o[k++] = 0;
+                    --i; --j;
                 }
-                else if (j < 0 || (i >= 0 && mv == 1)) { o[k++] = 1; --i; }
-                else { o[k++] = 2; --j; }
+                else if (j < 0 || (i >= 0 && mv == 1)) { if (emit) o[k++] = 1; --i; }
+                else { if (emit) o[k++] = 2; --j; }
             }
         }
         __syncwarp();
         park(buf ^ 1);
         __syncwarp();
     }
-    if (lane == 0) { n_ops[e] = k; res[e].len = n_cols; res[e].dist = n_diff; }
+    if (lane == 0) { if (emit) n_ops[e] = k; res[e].len = n_cols; res[e].dist = n_diff; }
 }
 
 }  // namespace pa

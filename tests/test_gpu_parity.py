@@ -432,6 +432,31 @@ def test_cta_per_pair_kernel_long_pairs(gpu, oracle):
         assert tuple(rev[k]) == tuple(oracle.align_forward(enc[ia[k]], enc[ib[k]])), (ia[k], ib[k])
 
 
+def test_few_long_pairs_take_the_cta_per_item_route(gpu, oracle, monkeypatch):
+    """A triangle range of long A/C/G/T pairs too small to fill the warp-per-item statistics kernel (config 5 cut over
+    several GPUs) runs on the move-storing CTA-per-item kernel, the walk counting the statistics: records equal the
+    oracle's and the warp kernel's (floating window) on the same pairs; sub-ranges and device-resident output too."""
+    _, seqs = synth.make_long(5, 901, length=9000, spread=0.08)
+    enc = [synth.to_masks(s) for s in seqs]
+    enc.append(enc[0][:8300].copy())
+    want = _oracle_all(oracle, enc, threads=12)
+    gpu.upload(enc)                      # 15 pairs: far too few for a warp each
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_cta_ms"] > 0 and t["walk_ms"] > 0 and t["dp_duo_ms"] == 0.0
+    _same(got, want)
+    _same(gpu.align_all_pairs(2, 9), want[2:11])
+    monkeypatch.setenv("PAIRALIGN_NO_CTA", "1")          # the warp-per-item kernel on the same pairs
+    gpu.init()
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["walk_ms"] == 0.0 and t["dp_cta_ms"] == 0.0
+    _same(got, want)
+    monkeypatch.delenv("PAIRALIGN_NO_CTA")
+    gpu.init()
+
+
 def test_all_four_dp_kernels_in_one_call(gpu, oracle):
     """s16x2 (short), int32 warp (4.6-8 kb), CTA (> 8 kb) and general (IUPAC) pairs from one upload."""
     _, short = synth.make_random(6, 601, 200, 900)
