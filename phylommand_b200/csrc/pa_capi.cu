@@ -917,7 +917,8 @@ static bool few_long_items(const Context &c, const pa_params &p, uint64_t count_
     const long long win_spread = 17ll * (std::llabs((long long)p.match) + std::llabs((long long)p.mismatch) +
                                          std::llabs((long long)p.gap_open) + std::llabs((long long)p.gap_ext));
     if (p.gap_ext < -1024 || win_spread > 3500 || max_len16(p) < 16) return false;
-    return c.force_cta || count_per_device / 2 < 6ull * (uint64_t)d.grid_duo_auto * WARPS_PER_CTA;
+    // measured on config 5 (profiles/r02_c5_routes.txt): 4975 items per device are better off on the warp kernel (4.2 per warp), 2487 are not
+    return c.force_cta || count_per_device / 2 < 4ull * (uint64_t)d.grid_duo_auto * WARPS_PER_CTA;
 }
 
 static int align_impl(const pa_params *params, uint64_t first, uint64_t count, const uint32_t *ia, const uint32_t *ib,
