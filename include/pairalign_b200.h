@@ -120,8 +120,8 @@ size_t pa_encode_sequence(const char *text, size_t len, uint8_t *out,
 
 /* Upload n_seq encoded sequences (one 4-bit mask per byte, concatenated;
  * sequence s is masks[offsets[s] .. offsets[s+1])) to every device of the
- * context.  The module packs them (2 bit/base for pure A/C/G/T sequences,
- * 4 bit/base otherwise) and keeps them resident until the next upload. */
+ * context.  The devices pack them (2 bit/base and 4 bit/base, pa_pack_kernel)
+ * and keep them resident until the next upload. */
 int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t n_seq);
 uint32_t pa_num_sequences(void);
 
@@ -145,12 +145,6 @@ int pa_align_all_pairs(const pa_params *params, uint64_t first, uint64_t count,
 /* Align an explicit list of pairs (ia[k], ib[k]) -> out[k]. */
 int pa_align_pairs(const pa_params *params, const uint32_t *ia, const uint32_t *ib,
                    uint64_t count, pa_pair_result *out);
-
-/* Same as pa_align_all_pairs but the results stay on device 0 of the context
- * (d_out: device pointer to count records) and nothing is copied back; used to
- * time the kernels with inputs and outputs resident in HBM. */
-int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t count,
-                              void *d_out);
 
 /* Alignment of one pair as pairalign -a prints it: get_x()/get_y() after
  * align() (src/seqpair.cpp:146-188, src/seqpair.h:83-84).  ax/ay receive
@@ -188,12 +182,6 @@ uint64_t pa_count_cells(uint64_t first, uint64_t count);
 
 int pa_get_timing(pa_timing *t);
 
-/* Device-free: the longest sequence the s16x2 kernel takes with plain 16-bit scores for these parameters
- * (longer A/C/G/T pairs use its floating-window form or the int32 kernels) and the bias it stores states with
- * (stored = true + bias; both 16-bit halves stay negative, see DESIGN.md section 5).  0 / 0 when the parameters
- * are outside the byte-table range (general kernel). */
-int pa_s16_limits(const pa_params *params, uint32_t *max_len, int32_t *bias);
-
 /* ---- per-pair statistics (host; the reference's exact expressions) -------- */
 
 /* similarity(false): len>0 ? 1.0-(dist/double(len)) : 1.0  (src/seqpair.cpp:272-273) */
@@ -229,7 +217,19 @@ int pa_nj_build(const float *dist, uint32_t n, pa_nj_join *joins, uint32_t *root
 /* Kernels launched and algorithmic bytes moved by the last pa_nj_build of this thread. */
 int pa_nj_last_stats(uint64_t *launches, uint64_t *bytes);
 
-/* ---- measurement support ---------------------------------------------------- */
+/* ---- measurement and test support (bench.py, tests/; not part of the drop-in surface) ---------- */
+
+/* Same as pa_align_all_pairs but the results stay on device 0 of the context
+ * (d_out: device pointer to count records) and nothing is copied back; used to
+ * time the kernels with inputs and outputs resident in HBM. */
+int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t count,
+                              void *d_out);
+
+/* Device-free: the longest sequence the s16x2 kernel takes with plain 16-bit scores for these parameters
+ * (longer A/C/G/T pairs use its floating-window form or the int32 kernels) and the bias it stores states with
+ * (stored = true + bias; both 16-bit halves stay negative, see DESIGN.md section 4).  0 / 0 when the parameters
+ * are outside the byte-table range (general kernel).  The tests use it to build inputs at the limit. */
+int pa_s16_limits(const pa_params *params, uint32_t *max_len, int32_t *bias);
 
 /* INT32 issue-rate micro-benchmark on device 0 of the context: independent
  * chains of the instruction classes the DP uses.  which: 0 IADD3, 1 VIMNMX3,
