@@ -443,7 +443,8 @@ def main() -> None:
 
     def roofline_of(r, name):
         dom = max(r["buckets"], key=lambda k: r["buckets"][k])
-        packed = dom == "dp_duo_ms"
+        # the CTA bucket holds the s16x2 move kernel when the walk ran (few long items), the int32 CTA kernel otherwise
+        packed = dom == "dp_duo_ms" or (dom == "dp_cta_ms" and r["buckets"]["walk_ms"] > 0)
         pk = peak_ops if packed else alu32
         # max over ranks of the kernel time against that rank's cells: use the slowest rank's figure (whole-job view)
         achieved = OPS_PER_CELL * (r["total_cells"] / world) / (r["kern_ms"] * 1e-3) / 1e9

@@ -84,6 +84,7 @@ struct Device {
     size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0, cap_items = 0;
     uint2 *d_items = nullptr;                 // work items of the move-storing s16x2 kernels (entries of the batch, in twos)
     int grid_moves_warp = 0, grid_moves_cta = 0;
+    bool moves_smem_set = false;
     // Events of one in-flight chunk (two chunks are in flight: slot = chunk & 1).  k[0]..k[1] s16x2 stage,
     // k[1]..k[2] 32-bit warp stage, k[2]..k[3] CTA-per-pair stage, k[3]..k[4] general stage; k[4] also releases the
     // D2H copy of the chunk on copy_stream, `done` marks its end (and lets the next kernel reuse d_out[slot]).
@@ -595,8 +596,45 @@ int pa_init(const int *devices, int n_dev) {
         d.n_sm = n_sm;
         c->dev.push_back(d);
     }
-    // Streams, events, scratch and the occupancy queries (which make the driver load every kernel of the module for that
-    // device) take a few hundred milliseconds per device: every device sets itself up on its own host thread.
+    struct { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_cta, fast, cta, gen, stats; } occ0 = {};
+    {
+    int occ = 0;
+    cudaError_t e2 = cudaSetDevice(c->dev[0].id);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
+    occ0.duo = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO, 3>, WARPS_PER_CTA * 32, 0);
+    occ0.duo3 = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
+    occ0.duo8 = std::max(1, occ);
+    // the two builds of a kernel (gap extension at run time / as an immediate) share one grid size: the smaller
+    int occ_c = 0;
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
+    occ0.duo_auto = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1, 12>, WARPS_PER_CTA * 32, 0);
+    occ0.sets = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
+    occ0.moves_warp = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
+    occ0.moves_cta = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
+    occ0.fast = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
+    occ0.cta = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
+    occ0.gen = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
+    occ0.stats = std::max(1, occ);
+    if (e2 != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e2);
+        delete c;
+        return fail(PA_ECUDA, "occupancy query failed: %s", msg.c_str());
+    }
+    }
+    // Streams, events and scratch: every device sets itself up on its own host thread.
     std::vector<cudaError_t> setup_err(c->dev.size(), cudaSuccess);
     auto setup = [&](size_t k) {
         Device &d = c->dev[k];
@@ -610,37 +648,12 @@ int pa_init(const int *devices, int n_dev) {
         }
         if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 5 * sizeof(unsigned long long));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
-        int occ = 0;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO, 3>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo3 = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo8 = std::max(1, occ) * d.n_sm;
-        // the two builds of a kernel (gap extension at run time / as an immediate) share one grid size: the smaller
-        int occ_c = 0;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
-        d.grid_duo_auto = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1, 12>, WARPS_PER_CTA * 32, 0);
-        d.grid_sets = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
-        d.grid_moves_warp = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
-        d.grid_moves_cta = std::max(1, std::min(occ, occ_c)) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
-        d.grid_fast = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
-        d.grid_cta = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
-        d.grid_gen = std::max(1, occ) * d.n_sm;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
-        d.grid_stats = std::max(1, occ) * d.n_sm;
+        // resident CTAs per SM of every kernel: asked once, on the first device (the query makes the driver load the kernel
+        // for that device, a few hundred milliseconds for the whole module; the devices of a context are the same chip)
+        d.grid_duo = occ0.duo * d.n_sm; d.grid_duo3 = occ0.duo3 * d.n_sm; d.grid_duo8 = occ0.duo8 * d.n_sm;
+        d.grid_duo_auto = occ0.duo_auto * d.n_sm; d.grid_sets = occ0.sets * d.n_sm;
+        d.grid_moves_warp = occ0.moves_warp * d.n_sm; d.grid_moves_cta = occ0.moves_cta * d.n_sm;
+        d.grid_fast = occ0.fast * d.n_sm; d.grid_cta = occ0.cta * d.n_sm; d.grid_gen = occ0.gen * d.n_sm; d.grid_stats = occ0.stats * d.n_sm;
         d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, d.grid_moves_warp), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
         setup_err[k] = e2;
     };
@@ -1158,6 +1171,11 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         }
         CU(cudaEventRecord(d.ev[3], d.stream));
         if (!h_items_long.empty()) {
+            if (!d.moves_smem_set) {      // more than 48 KB of dynamic shared memory needs the opt-in, once per device
+                CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM));
+                CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM));
+                d.moves_smem_set = true;
+            }
             if (prm.gap_ext == -1)
                 pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM, d.stream>>>(
                     S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
