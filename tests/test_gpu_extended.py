@@ -129,3 +129,41 @@ def test_command_line_on_config_prefixes_matches_the_reference(cli, tmp_path, ta
     assert r.stdout == (PREFIX / f"{tag}.out").read_bytes()
     if groups:
         assert (tmp_path / f"{tag}.fst.alignment_groups").read_bytes() == (PREFIX / f"{tag}.alignment_groups").read_bytes()
+
+
+def test_floating_window_on_structured_long_pairs(gpu, oracle, monkeypatch):
+    """The 16-bit floating window rests on an analytic bound (what a lane holds lies within a few hundred of its right
+    edge); inputs built to stress it -- a 2.5 kb deletion, a 2 kb poly-T insertion, poly-A, a 4-base repeat, the reverse --
+    at 9-10 kb, on both routes a long pair can take for its statistics (CTA per item with stored moves + walk; warp per
+    item carrying counters) and, for three of the pairs, as op strings."""
+    rng = np.random.default_rng(31337)
+    a = synth.BASES[rng.integers(0, 4, size=9500)]
+    seqs = [a, np.concatenate([a[:3500], a[6000:]]), np.concatenate([a[:4000], np.full(2000, ord("T"), dtype=np.uint8), a[4000:8500]]),
+            np.full(9000, ord("A"), dtype=np.uint8), np.frombuffer(b"ACGT" * 2400, dtype=np.uint8), a[::-1].copy()]
+    seqs[1] = np.concatenate([seqs[1], synth.BASES[rng.integers(0, 4, size=2000)]])        # keep every sequence above 8192
+    enc = [synth.to_masks(x) for x in seqs]
+    assert min(len(e) for e in enc) > 8192
+    masks, offsets = gpu.pack(enc)
+    want = oracle.all_pairs(masks, offsets, threads=15)
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_cta_ms"] > 0 and t["walk_ms"] > 0
+    assert got.tobytes() == want.tobytes()
+    monkeypatch.setenv("PAIRALIGN_NO_CTA", "1")
+    gpu.init()
+    gpu.upload(enc)
+    got = gpu.align_all_pairs()
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_cta_ms"] == 0.0
+    assert got.tobytes() == want.tobytes()
+    monkeypatch.delenv("PAIRALIGN_NO_CTA")
+    gpu.init()
+    gpu.upload(enc)
+    ia, ib = np.array([0, 0, 3]), np.array([1, 2, 4])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    for k in range(len(ia)):
+        r, w = oracle.align_ops(enc[ia[k]], enc[ib[k]], compact=True)
+        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
+        assert ops[int(off[k]):int(off[k]) + int(n_ops[k])].tobytes() == w.tobytes(), (ia[k], ib[k])
