@@ -83,7 +83,7 @@ struct Device {
     pa_pair_result *d_res = nullptr;
     size_t cap_dirs = 0, cap_ops = 0, cap_tb_pairs = 0, cap_items = 0;
     uint2 *d_items = nullptr;                 // work items of the move-storing s16x2 kernels (entries of the batch, in twos)
-    int grid_moves_warp = 0, grid_moves_cta = 0;
+    int grid_moves_warp = 0, grid_moves_warp_sets = 0, grid_moves_cta = 0;
     bool moves_smem_set = false;
     // Events of one in-flight chunk (two chunks are in flight: slot = chunk & 1).  k[0]..k[1] s16x2 stage,
     // k[1]..k[2] 32-bit warp stage, k[2]..k[3] CTA-per-pair stage, k[3]..k[4] general stage; k[4] also releases the
@@ -152,7 +152,7 @@ struct Context {
     uint8_t *host_masks = nullptr;         // the uploaded 4-bit sets, pinned: the devices pack from them (pa_pack_kernel)
     uint64_t host_masks_cap = 0;           // and pa_align_pair_traceback rebuilds strings from them
     std::vector<unsigned long long> host_offsets;     // offsets into host_masks (n_seq + 1)
-    std::vector<uint8_t> host_pure;
+    std::vector<uint8_t> host_pure, host_fastok;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     bool all_pure = true;
     bool all_fast = true;              // no sequence holds a gap character (everything can run on the s16x2 kernels)
@@ -596,7 +596,7 @@ int pa_init(const int *devices, int n_dev) {
         d.n_sm = n_sm;
         c->dev.push_back(d);
     }
-    struct { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_cta, fast, cta, gen, stats; } occ0 = {};
+    struct { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_warp_sets, moves_cta, fast, cta, gen, stats; } occ0 = {};
     {
     int occ = 0;
     cudaError_t e2 = cudaSetDevice(c->dev[0].id);
@@ -617,8 +617,11 @@ int pa_init(const int *devices, int n_dev) {
     if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
     if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
     occ0.moves_warp = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0, true, 0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1, true, 12>, WARPS_PER_CTA * 32, 0);
+    occ0.moves_warp_sets = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
     occ0.moves_cta = std::max(1, std::min(occ, occ_c));
     if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
     occ0.fast = std::max(1, occ);
@@ -652,9 +655,9 @@ int pa_init(const int *devices, int n_dev) {
         // for that device, a few hundred milliseconds for the whole module; the devices of a context are the same chip)
         d.grid_duo = occ0.duo * d.n_sm; d.grid_duo3 = occ0.duo3 * d.n_sm; d.grid_duo8 = occ0.duo8 * d.n_sm;
         d.grid_duo_auto = occ0.duo_auto * d.n_sm; d.grid_sets = occ0.sets * d.n_sm;
-        d.grid_moves_warp = occ0.moves_warp * d.n_sm; d.grid_moves_cta = occ0.moves_cta * d.n_sm;
+        d.grid_moves_warp = occ0.moves_warp * d.n_sm; d.grid_moves_warp_sets = occ0.moves_warp_sets * d.n_sm; d.grid_moves_cta = occ0.moves_cta * d.n_sm;
         d.grid_fast = occ0.fast * d.n_sm; d.grid_cta = occ0.cta * d.n_sm; d.grid_gen = occ0.gen * d.n_sm; d.grid_stats = occ0.stats * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, d.grid_moves_warp), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
+        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, std::max(d.grid_moves_warp, d.grid_moves_warp_sets)), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
         setup_err[k] = e2;
     };
     if (c->dev.size() == 1) setup(0);
@@ -845,6 +848,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     }
     c.n_seq = n_seq;
     c.host_pure = pure;
+    c.host_fastok = fastok;
     c.len = len;
     c.max_len = max_len;
     c.min_len = n_seq ? *std::min_element(len.begin(), len.end()) : 0;
@@ -1028,8 +1032,8 @@ int pa_align_all_pairs_device(const pa_params *params, uint64_t first, uint64_t 
 }
 
 // Bytes of the move store of one pair: n rows of P*W/4 bytes (W = 32*K slots per block), 128-byte aligned.
-static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool pure, bool fast) {
-    const uint64_t W = 32ull * ((pure && fast) ? KMOV : KGEN);
+static uint64_t dirs_bytes(uint32_t n, uint32_t m, bool moves_kernel) {
+    const uint64_t W = 32ull * (moves_kernel ? KMOV : KGEN);
     const uint64_t P = (m + W - 1) / W;
     const uint64_t bytes = (uint64_t)n * (P * W / 4);
     return (bytes + 127) / 128 * 128;
@@ -1062,8 +1066,16 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
     const SeqStore S = store_of(d, c.n_seq);
     const int threads = WARPS_PER_CTA * 32;
     std::vector<unsigned long long> h_dirs_off, h_ops_off;
-    std::vector<uint2> h_items, h_items_long;
+    std::vector<uint2> h_items[2][2];            // [long][sets]: work items of the four s16x2 move kernels
     const uint64_t wave_items = (uint64_t)d.grid_moves_cta;              // one wave of the CTA-per-item grid
+    // which kernel family takes a pair: 0 the general int32 kernel, 1 the s16x2 move kernels on 2-bit codes (both plain
+    // A/C/G/T), 2 the same on 4-bit sets (IUPAC codes, no gap character)
+    const bool sets_ok = prm.match >= prm.mismatch && !c.no_amb;
+    auto klass = [&](uint32_t a, uint32_t b) -> int {
+        if (!fast || !c.len[a] || !c.len[b]) return 0;
+        if (c.host_pure[a] && c.host_pure[b]) return 1;
+        return (sets_ok && c.host_fastok[a] && c.host_fastok[b]) ? 2 : 0;
+    };
     uint64_t s0 = lo;
     while (s0 < hi) {
         // one batch: as many pairs as the move store holds
@@ -1075,8 +1087,8 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         h_dirs_off.clear(); h_ops_off.clear();
         while (e0 < hi && e0 - s0 < (1ull << 20)) {
             const uint32_t a = ia[e0], b = ib[e0];
-            const bool pure = c.host_pure[a] && c.host_pure[b];
-            const uint64_t need = (c.len[a] && c.len[b]) ? dirs_bytes(c.len[a], c.len[b], pure, fast) : 0;
+            const int kl = klass(a, b);
+            const uint64_t need = (c.len[a] && c.len[b]) ? dirs_bytes(c.len[a], c.len[b], kl != 0) : 0;
             if (dbytes + need > budget) {
                 if (e0 == s0) return fail(PA_ENOMEM, "the moves of pair %llu need %llu bytes; %llu available", (unsigned long long)e0,
                                           (unsigned long long)need, (unsigned long long)budget);
@@ -1091,7 +1103,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             h_ops_off.push_back(obytes);
             dbytes += need;
             if (ops) obytes += (uint64_t)c.len[a] + c.len[b];
-            if (pure && fast && need) {      // same pairing rule as the item loop below: neighbours with the same first sequence
+            if (kl) {      // same pairing rule as the item loop below: neighbours with the same first sequence
                 const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
                 if (lng) ++n_long;
                 if (open && open_a == a && open_long == lng) open = false;
@@ -1104,25 +1116,29 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             if (n_long == e0 - s0 && n_long_items % wave_items == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
         }
         const uint64_t nb = e0 - s0;
-        // work items of the s16x2 kernels: neighbouring entries with the same first sequence go together
-        h_items.clear(); h_items_long.clear();
-        n_long = 0;
+        // work items of the s16x2 kernels: neighbouring entries with the same first sequence go together; an item with an
+        // ambiguous sequence runs on the set form
+        for (auto &row : h_items) for (auto &v : row) v.clear();
         for (uint64_t k = 0; k < nb; ++k) {
             const uint32_t a = ia[s0 + k], b = ib[s0 + k];
-            if (!(fast && c.host_pure[a] && c.host_pure[b] && c.len[a] && c.len[b])) continue;
+            int kl = klass(a, b);
+            if (!kl) continue;
             const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
             uint32_t second = 0xffffffffu;
             if (k + 1 < nb) {
                 const uint32_t a2 = ia[s0 + k + 1], b2 = ib[s0 + k + 1];
-                if (a2 == a && c.host_pure[b2] && c.len[b2] && (std::max(c.len[a], c.len[b2]) > LONG_LEN) == lng) second = (uint32_t)(k + 1);
+                const int kl2 = klass(a2, b2);
+                if (a2 == a && kl2 && (std::max(c.len[a], c.len[b2]) > LONG_LEN) == lng) { second = (uint32_t)(k + 1); kl = std::max(kl, kl2); }
             }
-            (lng ? h_items_long : h_items).push_back(make_uint2((uint32_t)k, second));
-            if (lng) n_long += second != 0xffffffffu ? 2 : 1;
+            h_items[lng ? 1 : 0][kl == 2 ? 1 : 0].push_back(make_uint2((uint32_t)k, second));
             if (second != 0xffffffffu) ++k;
         }
-        const bool route_long = !h_items_long.empty() && !c.no_cta &&
-                                (c.force_cta || h_items_long.size() < 4ull * (uint64_t)d.grid_moves_warp * WARPS_PER_CTA);
-        if (!route_long) { h_items.insert(h_items.end(), h_items_long.begin(), h_items_long.end()); h_items_long.clear(); }
+        const size_t n_long_it = h_items[1][0].size() + h_items[1][1].size();
+        const bool route_long = n_long_it && !c.no_cta && (c.force_cta || n_long_it < 4ull * (uint64_t)d.grid_moves_warp * WARPS_PER_CTA);
+        if (!route_long)
+            for (int z = 0; z < 2; ++z) { h_items[0][z].insert(h_items[0][z].end(), h_items[1][z].begin(), h_items[1][z].end()); h_items[1][z].clear(); }
+        size_t item_off[2][2], n_items_all = 0;
+        for (int l = 0; l < 2; ++l) for (int z = 0; z < 2; ++z) { item_off[l][z] = n_items_all; n_items_all += h_items[l][z].size(); }
         auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
             if (bytes <= cap && *ptr) return cudaSuccess;
             cudaFree(*ptr); *ptr = nullptr; cap = 0;
@@ -1132,7 +1148,7 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         };
         CU(grow((void **)&d.d_dirs, d.cap_dirs, std::max<uint64_t>(dbytes, 128)));
         CU(grow((void **)&d.d_ops, d.cap_ops, std::max<uint64_t>(obytes, 128)));
-        CU(grow((void **)&d.d_items, d.cap_items, std::max<size_t>(h_items.size() + h_items_long.size(), 1) * sizeof(uint2)));
+        CU(grow((void **)&d.d_items, d.cap_items, std::max<size_t>(n_items_all, 1) * sizeof(uint2)));
         if (nb > d.cap_tb_pairs) {
             cudaFree(d.d_dirs_off); cudaFree(d.d_ops_off); cudaFree(d.d_nops); cudaFree(d.d_res);
             d.d_dirs_off = d.d_ops_off = nullptr; d.d_nops = nullptr; d.d_res = nullptr; d.cap_tb_pairs = 0;
@@ -1152,38 +1168,56 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaMemcpyAsync(d.d_ib, ib + s0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_dirs_off, h_dirs_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.d_ops_off, h_ops_off.data(), nb * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
-        if (!h_items.empty())
-            CU(cudaMemcpyAsync(d.d_items, h_items.data(), h_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, d.stream));
-        if (!h_items_long.empty())
-            CU(cudaMemcpyAsync(d.d_items + h_items.size(), h_items_long.data(), h_items_long.size() * sizeof(uint2), cudaMemcpyHostToDevice, d.stream));
+        for (int l = 0; l < 2; ++l) for (int z = 0; z < 2; ++z)
+            if (!h_items[l][z].empty())
+                CU(cudaMemcpyAsync(d.d_items + item_off[l][z], h_items[l][z].data(), h_items[l][z].size() * sizeof(uint2), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemsetAsync(d.counters, 0, 5 * sizeof(unsigned long long), d.stream));
         CU(cudaMemsetAsync(d.d_res, 0, nb * sizeof(pa_pair_result), d.stream));
         CU(cudaEventRecord(d.ev[0], d.stream));
-        if (!h_items.empty()) {
-            if (prm.gap_ext == -1)
-                pa_warp_duo_moves_kernel<-1><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items, (uint32_t)h_items.size(), l16,
-                                                                                          d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
-            else
-                pa_warp_duo_moves_kernel<0><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items, (uint32_t)h_items.size(), l16,
-                                                                                         d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+        const bool gec = prm.gap_ext == -1, dc12 = gec && prm.match - prm.mismatch == 12;
+        // warp per item: plain (work counter 0), sets (counter 2)
+        if (!h_items[0][0].empty()) {
+            const uint32_t ni = (uint32_t)h_items[0][0].size();
+            if (gec) pa_warp_duo_moves_kernel<-1><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items + item_off[0][0], ni, l16,
+                                                                                      d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            else pa_warp_duo_moves_kernel<0><<<d.grid_moves_warp, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items + item_off[0][0], ni, l16,
+                                                                                 d.counters, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            CU(cudaGetLastError());
+            d.launches += 1;
+        }
+        if (!h_items[0][1].empty()) {
+            const uint32_t ni = (uint32_t)h_items[0][1].size();
+            if (dc12) pa_warp_duo_moves_kernel<-1, true, 12><<<d.grid_moves_warp_sets, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items + item_off[0][1], ni, l16,
+                                                                                                       d.counters + 2, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            else pa_warp_duo_moves_kernel<0, true, 0><<<d.grid_moves_warp_sets, threads, 0, d.stream>>>(S, sc, d.d_ia, d.d_ib, d.d_items + item_off[0][1], ni, l16,
+                                                                                                d.counters + 2, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
             CU(cudaGetLastError());
             d.launches += 1;
         }
         CU(cudaEventRecord(d.ev[3], d.stream));
-        if (!h_items_long.empty()) {
-            if (!d.moves_smem_set) {      // more than 48 KB of dynamic shared memory needs the opt-in, once per device
-                CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM));
-                CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVES_CTA_SMEM));
-                d.moves_smem_set = true;
-            }
-            if (prm.gap_ext == -1)
-                pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM, d.stream>>>(
-                    S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
-                    d.d_res, d.d_dirs, d.d_dirs_off);
-            else
-                pa_cta_duo_moves_kernel<0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, MOVES_CTA_SMEM, d.stream>>>(
-                    S, sc, d.d_ia, d.d_ib, d.d_items + h_items.size(), (uint32_t)h_items_long.size(), d.counters + 3, d.bbuf, d.bbuf_rows,
-                    d.d_res, d.d_dirs, d.d_dirs_off);
+        // CTA per item: plain (counter 3), sets (counter 4); more than 48 KB of dynamic shared memory needs the opt-in, once per device
+        if (n_long_it && route_long && !d.moves_smem_set) {
+            CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moves_cta_smem(false)));
+            CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moves_cta_smem(false)));
+            CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moves_cta_smem(true)));
+            CU(cudaFuncSetAttribute(pa_cta_duo_moves_kernel<-1, true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moves_cta_smem(true)));
+            d.moves_smem_set = true;
+        }
+        if (!h_items[1][0].empty()) {
+            const uint32_t ni = (uint32_t)h_items[1][0].size();
+            if (gec) pa_cta_duo_moves_kernel<-1><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, moves_cta_smem(false), d.stream>>>(
+                         S, sc, d.d_ia, d.d_ib, d.d_items + item_off[1][0], ni, d.counters + 3, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            else pa_cta_duo_moves_kernel<0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, moves_cta_smem(false), d.stream>>>(
+                     S, sc, d.d_ia, d.d_ib, d.d_items + item_off[1][0], ni, d.counters + 3, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            CU(cudaGetLastError());
+            d.launches += 1;
+        }
+        if (!h_items[1][1].empty()) {
+            const uint32_t ni = (uint32_t)h_items[1][1].size();
+            if (dc12) pa_cta_duo_moves_kernel<-1, true, 12><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, moves_cta_smem(true), d.stream>>>(
+                          S, sc, d.d_ia, d.d_ib, d.d_items + item_off[1][1], ni, d.counters + 4, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
+            else pa_cta_duo_moves_kernel<0, true, 0><<<d.grid_moves_cta, MOVES_CTA_WARPS * 32, moves_cta_smem(true), d.stream>>>(
+                     S, sc, d.d_ia, d.d_ib, d.d_items + item_off[1][1], ni, d.counters + 4, d.bbuf, d.bbuf_rows, d.d_res, d.d_dirs, d.d_dirs_off);
             CU(cudaGetLastError());
             d.launches += 1;
         }
@@ -1196,7 +1230,8 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         }
         CU(cudaEventRecord(d.ev[1], d.stream));
         pa_walk_kernel<<<(unsigned)((nb + WALK_WARPS - 1) / WALK_WARPS), WALK_WARPS * 32, 0, d.stream>>>(S, d.d_ia, d.d_ib, nb, d.d_res, d.d_dirs, d.d_dirs_off,
-                                                                        ops ? d.d_ops : nullptr, d.d_ops_off, d.d_nops, KMOV, KGEN);
+                                                                        ops ? d.d_ops : nullptr, d.d_ops_off, d.d_nops,
+                                                                        fast ? KMOV : KGEN, (fast && sets_ok) ? KMOV : KGEN, KGEN);
         CU(cudaGetLastError());
         d.launches += 1;
         CU(cudaEventRecord(d.ev[2], d.stream));
@@ -1213,8 +1248,8 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
         CU(cudaEventElapsedTime(&warp_ms, d.ev[0], d.ev[3]));
         CU(cudaEventElapsedTime(&cta_ms, d.ev[3], d.ev[4]));
         kernel_ms[0] += dp_ms; kernel_ms[1] += walk_ms;
-        if (!h_items.empty()) d.duo_ms += warp_ms;
-        if (!h_items_long.empty()) d.cta_ms += cta_ms;
+        if (!h_items[0][0].empty() || !h_items[0][1].empty()) d.duo_ms += warp_ms;
+        if (n_long_it && route_long) d.cta_ms += cta_ms;
         if (any_general) d.gen_ms += dp_ms - warp_ms - cta_ms;
         // the walk wrote each op string backwards (the reference reverses at src/seqpair.cpp:183-188)
         if (ops) for (uint64_t k = s0; k < e0; ++k) std::reverse(ops + op_offsets[k], ops + op_offsets[k] + n_ops[k]);

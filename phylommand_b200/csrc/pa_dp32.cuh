@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32)
 pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const uint64_t count,
                pa_pair_result *res, const uint8_t *dirs, const unsigned long long *dirs_off,
                uint8_t *ops, const unsigned long long *ops_off, uint32_t *n_ops,
-               const int k_pure, const int k_general) {
+               const int k_pure, const int k_amb, const int k_general) {
     __shared__ __align__(16) uint4 win[WALK_WARPS][2][WALK_EPOCH][2];
     __shared__ int wbase[WALK_WARPS][2][WALK_EPOCH];
     const int lane = threadIdx.x & 31;
@@ -461,7 +461,8 @@ pa_walk_kernel(const SeqStore S, const uint32_t *ia, const uint32_t *ib, const u
     }
     const uint32_t *x4 = S.p4 + S.off4[a], *y4 = S.p4 + S.off4[b];
     uint32_t n_cols = 0, n_diff = 0;
-    const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : k_general);
+    // strip width of the kernel that stored this pair's moves: plain A/C/G/T, IUPAC codes without gap characters, the rest
+    const int W = 32 * ((S.pure[a] && S.pure[b]) ? k_pure : (S.fastok[a] && S.fastok[b]) ? k_amb : k_general);
     const int P = (m + W - 1) / W;
     const int padL = P * W - m;
     const int slots = P * W;                 // >= 256

@@ -33,6 +33,7 @@
 #pragma once
 
 #include "pa_dp32.cuh"
+#include "pa_dp_sets.cuh"
 
 namespace pa {
 
@@ -44,8 +45,10 @@ constexpr int MOVES_CTA_WARPS = 12;      // warps per item in the CTA form: 3 pe
 constexpr int MOVES_DELAY = 8;            // depth of a lane's delay ring (steps): 32-byte sector / 4-byte word
 constexpr int MOVES_RING_ROWS = 128;     // rows per shared-memory edge ring (11 rings + the staged x stay below 48 KB)
 using MovesRing = RingEdgeT<MOVES_RING_ROWS>;
-constexpr size_t MOVES_CTA_SMEM = (size_t)XSTAGE_WORDS * 4 + (size_t)(MOVES_CTA_WARPS - 1) * MOVES_RING_ROWS * 16 +
-                                  (size_t)MOVES_CTA_WARPS * 2 * MOVES_DELAY * 32 * 8;
+constexpr size_t moves_cta_smem(const bool sets) {
+    return (size_t)(sets ? 2 : 1) * XSTAGE_WORDS * 4 + (size_t)(MOVES_CTA_WARPS - 1) * MOVES_RING_ROWS * 16 +
+           (size_t)MOVES_CTA_WARPS * 2 * MOVES_DELAY * 32 * 8;
+}
 
 template <int K, int GEC = 0>
 __device__ __forceinline__ void duo_moves_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
@@ -69,6 +72,40 @@ __device__ __forceinline__ void duo_moves_row(const uint32_t (&Hs)[K], uint32_t 
         (void)vibmax_s16x2(h, g, pDhi, pDlo);                     // h >= max(gy, gx)
         // @!p IMAD mv, mv, one, imm.  Measured alternatives (profiles/r02_add_placement.txt): written as one * imm + mv, ptxas
         // strength-reduces the power of two and selects / adds on the ALU pipe instead: 34 -> 60 ms on the 1.5 kb set
+        m1 = pDlo ? m1 : m1 * one + (1u << (2 * k));
+        m1 = pUlo ? m1 : m1 * one + (2u << (2 * k));
+        m2 = pDhi ? m2 : m2 * one + (1u << (2 * k));
+        m2 = pUhi ? m2 : m2 * one + (2u << (2 * k));
+        Hdg = Hs[k];
+        Hd[k] = h; Gy[k] = gy;
+        Gl = gx;
+    }
+    Hout = Hd[K - 1]; Gxout = Gl; mv1 = m1; mv2 = m2;
+}
+
+// The same row on 4-bit base SETS (sequences with IUPAC codes, no gap character): hit vectors and pre-borrowed
+// column scores as in sets_row (pa_dp_sets.cuh), moves as above.
+template <int K, int GEC = 0, int DC = 0>
+__device__ __forceinline__ void duo_moves_row_sets(const uint32_t (&Hs)[K], uint32_t (&Hd)[K], uint32_t (&Gy)[K],
+                                                   const uint32_t (&HV)[K], const uint32_t (&XAc)[K], const uint32_t rowset,
+                                                   const uint32_t Dmul, const uint32_t GOc, const uint32_t GEpk, const uint32_t one,
+                                                   uint32_t hdiag, uint32_t Gl, uint32_t &Hout, uint32_t &Gxout,
+                                                   uint32_t &mv1, uint32_t &mv2) {
+    static_assert(K <= 16, "the moves of one lane must fit 32 bits");
+    const uint32_t GE2 = GEC ? ((uint32_t)GEC & 0xffffu) * 0x10001u : GEpk;
+    uint32_t Hdg = hdiag, m1 = 0, m2 = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t t2 = (HV[k] >> rowset) & 0x00010001u;
+        const uint32_t Gu = Gy[k];
+        const uint32_t m3x = __vimax3_s16x2(Hdg, Gu, Gl) + XAc[k];
+        const uint32_t h = __vadd2(DC ? t2 * (uint32_t)DC : t2 * Dmul, m3x);
+        const uint32_t o = Hdg * one + GOc;
+        const uint32_t gy = __viaddmax_s16x2(Gu, GE2, o);
+        const uint32_t gx = __viaddmax_s16x2(Gl, GE2, o);
+        bool pUhi, pUlo, pDhi, pDlo;
+        const uint32_t g = vibmax_s16x2(gy, gx, pUhi, pUlo);
+        (void)vibmax_s16x2(h, g, pDhi, pDlo);
         m1 = pDlo ? m1 : m1 * one + (1u << (2 * k));
         m1 = pUlo ? m1 : m1 * one + (2u << (2 * k));
         m2 = pDhi ? m2 : m2 * one + (1u << (2 * k));
@@ -110,7 +147,9 @@ __device__ __forceinline__ void build_tab_duo(int4 *tab, const Scoring sc, const
 // stored values and the 32-bit offsets of the frame they were stored in (true value = stored + offset).
 // dirp1 / dirp2: this lane's word of row 0 of the block in each pair's move store (nullptr: the pair has no column in
 // this block, or its moves are not wanted); dstride: words per row.
-template <int K, class Edge, bool WIN, int GEC>
+// SETS: xs / ys1 / ys2 are 4-bit sets (8 per word) and a cell scores by intersection; tab is not used and row 0 is set in
+// closed form (H = s, Gy = Gx = 0: the move is diagonal iff s >= 0, else up).
+template <int K, class Edge, bool WIN, int GEC, bool SETS = false, int DC = 0>
 __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n, const uint32_t *ys1, const uint32_t *ys2,
                                                 const int j_base1, const int j_base2, const bool last_block, const Scoring sc,
                                                 const int4 *tab, const Edge &edge, const int lane, BestDuo &best,
@@ -123,21 +162,31 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
     const uint32_t GOc = sc.go ? pack16(sc.go, sc.go - 1) : 0u, GEpk = pack16(sc.ge, sc.ge);
     const uint32_t one = (uint32_t)sc.one;
     const int j01 = j_base1 + lane * K, j02 = j_base2 + lane * K;
-    uint32_t HX[K], HY[K], Gy[K], selS[K];
+    const uint32_t Dmul = (uint32_t)(sc.match - sc.mismatch);
+    uint32_t HX[K], HY[K], Gy[K], selS[K];          // SETS: selS holds the hit vectors
+    uint32_t XAc[SETS ? K : 1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j1 = j01 + k, j2 = j02 + k;
         HX[k] = HinitPk; HY[k] = HinitPk; Gy[k] = Bpk;
-        const uint32_t c1 = j1 < 0 ? 5u : (j1 == 0 ? 4u : fetch2(ys1, j1));
-        const uint32_t c2 = j2 < 0 ? 5u : (j2 == 0 ? 6u : fetch2(ys2, j2));
-        selS[k] = ((8u | c2) << 12) | (c2 << 8) | ((8u | c1) << 4) | c1;
+        if constexpr (SETS) {
+            const uint32_t c1 = j1 >= 0 ? fetch4(ys1, j1) : 0u, c2 = j2 >= 0 ? fetch4(ys2, j2) : 0u;
+            selS[k] = hit_vector(c1) | (hit_vector(c2) << 16);
+            const int xa1 = j1 < 0 ? 0 : sc.mismatch + (j1 == 0 ? sc.go : 0);
+            const int xa2 = j2 < 0 ? 0 : sc.mismatch + (j2 == 0 ? sc.go : 0);
+            XAc[k] = pack16(xa1, xa2 - (xa1 < 0 ? 1 : 0));
+        } else {
+            const uint32_t c1 = j1 < 0 ? 5u : (j1 == 0 ? 4u : fetch2(ys1, j1));
+            const uint32_t c2 = j2 < 0 ? 5u : (j2 == 0 ? 6u : fetch2(ys2, j2));
+            selS[k] = ((8u | c2) << 12) | (c2 << 8) | ((8u | c1) << 4) | c1;
+        }
     }
     uint32_t hprev = HinitPk;
     uint32_t HoA = HinitPk, GoA = Bpk, HoB = HinitPk, GoB = Bpk;
     int off1 = -B, off2 = -B;                         // true value = stored + off
     uint32_t colBestPk = 0x80008000u;                 // !WIN: last-column maxima of both pairs, packed like the scores
     const int n_steps = ((n + 1) >> 1) + 31;
-    const int x_last_word = (n - 1) >> 4;
+    const int x_last_word = SETS ? (n - 1) >> 3 : (n - 1) >> 4;
     constexpr int CHUNK_STEPS = CHUNK_ROWS / 2;
 
     edge.acquire(min(n, 2 * CHUNK_ROWS), lane);
@@ -168,14 +217,34 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
         }
         fA = edge.load(min(2 * t + 2, n - 1));
         fB = edge.load(min(2 * t + 3, n - 1));
-        const uint32_t xi2 = (xw >> ((iA & 15) * 2)) & 15u;
-        xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
+        // codes of rows iA and iA + 1: two 2-bit codes, or (SETS) two 4-bit sets
+        const uint32_t xi2 = SETS ? (xw >> ((iA & 7) * 4)) & 0xffu : (xw >> ((iA & 15) * 2)) & 15u;
+        xw = xs[min(max(iA + 2, 0) >> (SETS ? 3 : 4), x_last_word)];
         uint2 mvP1 = make_uint2(0u, 0u), mvP2 = mvP1;      // moves of rows iA (x) and iA + 1 (y), pair 1 and pair 2
         if (iA >= 0 && iA < n) {
             const bool store = (lane == 31) && edge.has_sink();
             {
-                const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
-                duo_moves_row<K, GEC>(HX, HY, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hprev, ginA, HoA, GoA, mvP1.x, mvP2.x);
+                if constexpr (SETS) {
+                    if (iA == 0) {      // first row in closed form (values in this lane's frame: off = -B here)
+                        const bool dM = sc.match >= 0, dX = sc.mismatch >= 0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const uint32_t t2 = (selS[k] >> (xi2 & 15u)) & 0x00010001u;
+                            const bool real1 = j01 + k >= 0, real2 = j02 + k >= 0;
+                            const bool hit1 = (t2 & 1u) != 0, hit2 = (t2 >> 16) != 0;
+                            HY[k] = pack16(real1 ? (hit1 ? sc.match : sc.mismatch) + B : Hinit, real2 ? (hit2 ? sc.match : sc.mismatch) + B : Hinit);
+                            Gy[k] = Bpk;
+                            if (!(hit1 ? dM : dX)) mvP1.x |= 1u << (2 * k);       // not diagonal -> up (Gy = Gx = 0)
+                            if (!(hit2 ? dM : dX)) mvP2.x |= 1u << (2 * k);
+                        }
+                        HoA = HY[K - 1]; GoA = Bpk;
+                    } else {
+                        duo_moves_row_sets<K, GEC, DC>(HX, HY, Gy, selS, XAc, xi2 & 15u, Dmul, GOc, GEpk, one, hprev, ginA, HoA, GoA, mvP1.x, mvP2.x);
+                    }
+                } else {
+                    const int4 T = tab[(iA == 0 ? 4 : 0) + (xi2 & 3u)];
+                    duo_moves_row<K, GEC>(HX, HY, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hprev, ginA, HoA, GoA, mvP1.x, mvP2.x);
+                }
                 if (store) edge.store(iA, make_int4((int)HoA, (int)GoA, off1, off2));
                 if (last_block) {
                     if (WIN) {
@@ -191,8 +260,12 @@ __device__ __forceinline__ void block_duo_moves(const uint32_t *xs, const int n,
                 }
             }
             if (iA + 1 < n) {
-                const int4 T = tab[xi2 >> 2];
-                duo_moves_row<K, GEC>(HY, HX, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hinA, ginB, HoB, GoB, mvP1.y, mvP2.y);
+                if constexpr (SETS) {
+                    duo_moves_row_sets<K, GEC, DC>(HY, HX, Gy, selS, XAc, xi2 >> 4, Dmul, GOc, GEpk, one, hinA, ginB, HoB, GoB, mvP1.y, mvP2.y);
+                } else {
+                    const int4 T = tab[xi2 >> 2];
+                    duo_moves_row<K, GEC>(HY, HX, Gy, selS, (uint32_t)T.x, (uint32_t)T.y, GOc, GEpk, one, hinA, ginB, HoB, GoB, mvP1.y, mvP2.y);
+                }
                 if (store) edge.store(iA + 1, make_int4((int)HoB, (int)GoB, off1, off2));
                 if (last_block) {
                     if (WIN) {
@@ -292,7 +365,8 @@ __device__ __forceinline__ MovesItem load_moves_item(const SeqStore &S, const ui
     return r;
 }
 
-template <int GEC = 0>
+// SETS: the items hold a sequence with IUPAC codes (none with a gap character): 4-bit sets instead of 2-bit codes.
+template <int GEC = 0, bool SETS = false, int DC = 0>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MOVES_WARP_MINB)
 pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint2 *items,
                          const uint32_t n_items, const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all,
@@ -313,10 +387,17 @@ pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia,
         if (w >= n_items) break;
         const MovesItem it = load_moves_item(S, ia, ib, items[w]);
         __syncwarp();
-        const uint32_t *xs = stage_seq(S.p2 + S.off2[it.a], (uint32_t)(it.n + 15) >> 4, stage[wib][0], lane);
-        const uint32_t *ys1 = stage_seq(S.p2 + S.off2[it.y1], (uint32_t)(it.m1 + 15) >> 4, stage[wib][1], lane);
-        const uint32_t *ys2 = stage_seq(S.p2 + S.off2[it.y2], (uint32_t)(it.m2 + 15) >> 4, stage[wib][2], lane);
-        build_tab_duo(tabs[wib], sc, fetch2(S.p2 + S.off2[it.y1], 0), fetch2(S.p2 + S.off2[it.y2], 0), lane);
+        const uint32_t *xs, *ys1, *ys2;
+        if (SETS) {
+            xs = stage_seq(S.p4 + S.off4[it.a], (uint32_t)(it.n + 7) >> 3, stage[wib][0], lane);
+            ys1 = stage_seq(S.p4 + S.off4[it.y1], (uint32_t)(it.m1 + 7) >> 3, stage[wib][1], lane);
+            ys2 = stage_seq(S.p4 + S.off4[it.y2], (uint32_t)(it.m2 + 7) >> 3, stage[wib][2], lane);
+        } else {
+            xs = stage_seq(S.p2 + S.off2[it.a], (uint32_t)(it.n + 15) >> 4, stage[wib][0], lane);
+            ys1 = stage_seq(S.p2 + S.off2[it.y1], (uint32_t)(it.m1 + 15) >> 4, stage[wib][1], lane);
+            ys2 = stage_seq(S.p2 + S.off2[it.y2], (uint32_t)(it.m2 + 15) >> 4, stage[wib][2], lane);
+            build_tab_duo(tabs[wib], sc, fetch2(S.p2 + S.off2[it.y1], 0), fetch2(S.p2 + S.off2[it.y2], 0), lane);
+        }
         const bool win = (uint32_t)it.n > max_len16 || (uint32_t)it.m1 > max_len16 || (uint32_t)it.m2 > max_len16;
         const int B = win ? WIN_BIAS : sc.bias16;
         if (lane == 0) __stcg(&bbuf[vrow], make_int4((int)pack16(-sc.go + B, -sc.go + B), (int)pack16(B, B), -B, -B));
@@ -335,10 +416,10 @@ pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia,
             const int b1 = p - (P - P1), b2 = p - (P - P2);      // block index in each pair's own geometry
             uint32_t *q1 = b1 >= 0 ? d1 + b1 * 32 + lane : nullptr;
             uint32_t *q2 = (it.two && b2 >= 0) ? d2 + b2 * 32 + lane : nullptr;
-            if (win) block_duo_moves<KMOV, GlobalEdge, true, GEC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
-                                                                  edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
-            else block_duo_moves<KMOV, GlobalEdge, false, GEC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
-                                                               edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
+            if (win) block_duo_moves<KMOV, GlobalEdge, true, GEC, SETS, DC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
+                                                                            edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
+            else block_duo_moves<KMOV, GlobalEdge, false, GEC, SETS, DC>(xs, it.n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tabs[wib],
+                                                                         edge, lane, best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays[wib]);
         }
         best.colBest1 = __shfl_sync(FULL_MASK, best.colBest1, 31); best.colI1 = __shfl_sync(FULL_MASK, best.colI1, 31);
         best.colBest2 = __shfl_sync(FULL_MASK, best.colBest2, 31); best.colI2 = __shfl_sync(FULL_MASK, best.colI2, 31);
@@ -351,17 +432,19 @@ pa_warp_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia,
 
 // One item per CTA.  gedge_all: per CTA one column of n rows for the wrap-around edge (last warp -> first warp's next
 // block) plus the virtual row.  Always the floating-window form (only pairs beyond LONG_LEN come here).
-template <int GEC = 0>
+template <int GEC = 0, bool SETS = false, int DC = 0>
 __global__ void __launch_bounds__(MOVES_CTA_WARPS * 32, 1)
 pa_cta_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, const uint32_t *ib, const uint2 *items,
                         const uint32_t n_items, unsigned long long *work_counter, int4 *gedge_all, const uint32_t gedge_rows,
                         pa_pair_result *out, uint8_t *dirs, const unsigned long long *dirs_off) {
     constexpr int NW = MOVES_CTA_WARPS;
-    // dynamic shared memory (MOVES_CTA_SMEM bytes, above the 48 KB a kernel gets statically): x, the edge rings, the delay rings
+    // dynamic shared memory (moves_cta_smem(SETS) bytes, above the 48 KB a kernel gets statically): x (twice the words as
+    // 4-bit sets), the edge rings, the delay rings
+    constexpr int XW = SETS ? 2 * XSTAGE_WORDS : XSTAGE_WORDS;
     extern __shared__ __align__(16) unsigned char moves_smem[];
     uint32_t *xstage = reinterpret_cast<uint32_t *>(moves_smem);
-    int4 (*rings)[MOVES_RING_ROWS] = reinterpret_cast<int4 (*)[MOVES_RING_ROWS]>(moves_smem + XSTAGE_WORDS * 4);
-    uint2 *delays = reinterpret_cast<uint2 *>(moves_smem + XSTAGE_WORDS * 4 + (NW - 1) * MOVES_RING_ROWS * 16);
+    int4 (*rings)[MOVES_RING_ROWS] = reinterpret_cast<int4 (*)[MOVES_RING_ROWS]>(moves_smem + XW * 4);
+    uint2 *delays = reinterpret_cast<uint2 *>(moves_smem + XW * 4 + (NW - 1) * MOVES_RING_ROWS * 16);
     __shared__ int4 tab[8];
     __shared__ int prod[NW], cons[NW];
     __shared__ unsigned long long item_s;
@@ -381,13 +464,14 @@ pa_cta_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, 
         if (wi >= n_items) break;
         const MovesItem it = load_moves_item(S, ia, ib, items[wi]);
         {
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(S.p2 + S.off2[it.a]);
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(SETS ? S.p4 + S.off4[it.a] : S.p2 + S.off2[it.a]);
             uint4 *s4 = reinterpret_cast<uint4 *>(xstage);
-            const uint32_t n4 = (((uint32_t)(it.n + 15) >> 4) + 3) >> 2;
+            const uint32_t n4 = ((SETS ? (uint32_t)(it.n + 7) >> 3 : (uint32_t)(it.n + 15) >> 4) + 3) >> 2;
             for (uint32_t q = threadIdx.x; q < n4; q += blockDim.x) s4[q] = __ldg(&g4[q]);
         }
-        const uint32_t *ys1 = S.p2 + S.off2[it.y1], *ys2 = S.p2 + S.off2[it.y2];
-        if (w == 0) build_tab_duo(tab, sc, fetch2(ys1, 0), fetch2(ys2, 0), lane);
+        const uint32_t *ys1 = SETS ? S.p4 + S.off4[it.y1] : S.p2 + S.off2[it.y1];
+        const uint32_t *ys2 = SETS ? S.p4 + S.off4[it.y2] : S.p2 + S.off2[it.y2];
+        if (!SETS && w == 0) build_tab_duo(tab, sc, fetch2(ys1, 0), fetch2(ys2, 0), lane);
         if (threadIdx.x < NW) { prod[threadIdx.x] = 0; cons[threadIdx.x] = 0; }
         if (threadIdx.x == 0) {
             __stcg(&gedge[vrow], make_int4((int)pack16(-sc.go + B, -sc.go + B), (int)pack16(B, B), -B, -B));
@@ -421,7 +505,7 @@ pa_cta_duo_moves_kernel(const SeqStore S, const Scoring sc, const uint32_t *ia, 
             const int b1 = p - (P - P1), b2 = p - (P - P2);
             uint32_t *q1 = b1 >= 0 ? d1 + b1 * 32 + lane : nullptr;
             uint32_t *q2 = (it.two && b2 >= 0) ? d2 + b2 * 32 + lane : nullptr;
-            block_duo_moves<KMOV, MovesRing, true, GEC>(xstage, n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tab, edge, lane,
+            block_duo_moves<KMOV, MovesRing, true, GEC, SETS, DC>(xstage, n, ys1, ys2, p * W - pad1, p * W - pad2, p == P - 1, sc, tab, edge, lane,
                                                        best, q1, (uint32_t)P1 * 32u, q2, (uint32_t)P2 * 32u, delays + w * 2 * MOVES_DELAY * 32);
         }
         if (lane == 0) { bRow1[w] = best.rowBest1; bJ1[w] = best.rowJ1; bRow2[w] = best.rowBest2; bJ2[w] = best.rowJ2; }

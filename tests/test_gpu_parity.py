@@ -503,6 +503,44 @@ def test_batched_alignments(gpu, oracle):
         assert ax == wx.tolist() and ay == wy.tolist(), (ia[k], ib[k])
 
 
+def test_batched_alignments_with_iupac_codes_on_the_set_form(gpu, oracle):
+    """pairalign -a for sequences with IUPAC codes (no gap character): the move-storing s16x2 kernels in their 4-bit-set
+    form -- warp per item for short pairs, floating window above the 16-bit limit, CTA per item above 8192 -- against the
+    oracle's walk; plain and ambiguous entries mixed in one list, single-entry items, both orientations."""
+    rng = np.random.default_rng(77)
+    amb = np.frombuffer(b"ACGTRYSWKMBDHVN", dtype=np.uint8)
+    _, short = synth.make_random(8, 705, 3, 800, iupac=0.08)
+    enc = [gpu.encode("N" + synth.to_text(s)) for s in short]
+    enc = [e if len(e) else np.array([15], dtype=np.uint8) for e in enc]
+    enc.append(synth.to_masks(amb[rng.integers(0, len(amb), size=513)]))         # dense codes, one column past a block
+    _, plain = synth.make_random(2, 706, 100, 600)
+    enc += [synth.to_masks(s) for s in plain]
+    _, longs = synth.make_long(3, 707, length=5200, spread=0.1, div_lo=0.0, div_hi=0.08)
+    for s_ in longs[:2]:
+        s_ = s_.copy(); k = rng.random(len(s_)) < 0.03; s_[k] = amb[rng.integers(4, len(amb), size=int(k.sum()))]
+        enc.append(synth.to_masks(s_))
+    _, very = synth.make_long(3, 708, length=8800, spread=0.05)
+    for s_ in very:
+        s_ = s_.copy(); k = rng.random(len(s_)) < 0.02; s_[k] = amb[rng.integers(4, len(amb), size=int(k.sum()))]
+        enc.append(synth.to_masks(s_))
+    gpu.upload(enc)
+    n = len(enc)
+    short_n = 11
+    pairs = [(a, b) for a in range(short_n) for b in range(short_n) if a != b]
+    pairs += [(11, 12), (12, 11), (11, 3), (13, 14), (13, 15), (14, 15), (15, 13), (13, 0)]
+    ia, ib = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
+    lens = np.array([len(e) for e in enc])
+    ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+    t = gpu.timing()
+    assert t["dp_duo_ms"] > 0 and t["dp_cta_ms"] > 0 and t["dp_general_ms"] == 0.0 and t["walk_ms"] > 0
+    stats = gpu.align_pairs(ia, ib)
+    assert res.tobytes() == stats.tobytes()
+    for k in range(len(ia)):
+        r, want = oracle.align_ops(enc[ia[k]], enc[ib[k]], compact=max(lens[ia[k]], lens[ib[k]]) > 3000)
+        assert tuple(res[k]) == tuple(r), (ia[k], ib[k])
+        assert ops[int(off[k]):int(off[k]) + int(n_ops[k])].tobytes() == want.tobytes(), (ia[k], ib[k])
+
+
 def test_batched_alignments_long_pairs_take_a_cta(gpu, oracle):
     """pairalign -a for pairs longer than 8192: pa_cta32_kernel<16, true> (eight warps per pair, moves stored by
     every block) next to the one-pair-per-warp kernel for the shorter pairs of the same batch, walked back by
