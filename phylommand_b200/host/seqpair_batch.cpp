@@ -38,13 +38,16 @@ std::string SeqpairBatch::text(size_t s) const {
 }
 
 void SeqpairBatch::render(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, std::string &x, std::string &y) const {
+    x.resize(n_ops);
+    y.resize(n_ops);
+    if (n_ops) render_into(a, b, ops, n_ops, &x[0], &y[0]);
+}
+
+void SeqpairBatch::render_into(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, char *px, char *py) const {
     // translate_to_string (src/seqpair.cpp:62-72) through a 16-entry table: this loop writes every character of
     // pairalign -a's output (1.2 GB for 200 x 30 kb)
     static const struct Lut { char c[16]; Lut() { for (int m = 0; m < 16; ++m) c[m] = pa_mask_to_char((uint8_t)m); } } lut;
     const uint8_t *ma = masks(a), *mb = masks(b);
-    x.resize(n_ops);
-    y.resize(n_ops);
-    char *px = &x[0], *py = &y[0];
     size_t i = 0, j = 0;
     for (uint32_t k = 0; k < n_ops; ++k) {
         const uint8_t o = ops[k];

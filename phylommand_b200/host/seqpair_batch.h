@@ -51,6 +51,8 @@ public:
     void alignments(const pa_params &p, const std::vector<uint32_t> &ia, const std::vector<uint32_t> &ib, OpBatch &out);
     // turn one op string into the two printed lines
     void render(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, std::string &x, std::string &y) const;
+    // the same into caller-owned memory (n_ops characters each): lets several host threads fill one output buffer
+    void render_into(uint32_t a, uint32_t b, const uint8_t *ops, uint32_t n_ops, char *px, char *py) const;
 
 private:
     std::vector<uint8_t> masks_;

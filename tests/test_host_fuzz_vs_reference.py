@@ -85,7 +85,7 @@ def make_case(seed, group):
 
 
 MODES = [["-j", "-n", "-m"], ["-d", "-n"], ["-d", "-m"], ["-p", "-m", "-n"], ["-s"], ["-i", "-n", "-m"], ["-a", "-n"], ["-a"],
-         ["-j"], ["-A", "-p", "-n", "-m"], ["-A", "-d", "-n"]]
+         ["-j"], ["-A", "-p", "-n", "-m"], ["-A", "-d", "-n"], ["-m", "-a", "-n"], ["-m", "-a"], ["-a", "-v"]]
 GROUP_MODES = [["-g", "alignment_groups"], ["-g", "both:cut-off=0.9"], ["-g", "both:cut-off=0.97"], ["-g", "cluster:cut-off=0.9"],
                ["-g", "both"], ["-g", "alignment_groups", "-m", "-n"], ["-g", "both:cut-off=0.8", "-n"]]
 
