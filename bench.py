@@ -54,7 +54,7 @@ METRIC = "pairs/sec (all-pairs pairalign: seqpair DP + per-pair distance statist
 #: the DP kernel behind each pa_timing bucket
 KERNELS = {
     "dp_duo_ms": "pa_warp_duo_kernel (s16x2 DPX, two pairs per warp, two rows per step, strip width 8-13 columns per "
-                 "lane per work item; floating 16-bit window for pairs beyond int16; AMB variant for sparse IUPAC codes)",
+                 "lane per work item; floating 16-bit window for pairs beyond int16) / pa_warp_sets_kernel (the same recurrence on 4-bit IUPAC sets) when sequences carry ambiguity codes",
     "dp_fast_ms": "pa_warp32_kernel<16> (int32, one pair per warp)",
     "dp_cta_ms": "pa_cta_duo_moves_kernel (s16x2 with stored moves, one two-pair item per CTA, shared-memory ring edges; statistics "
                  "by the walk) or pa_cta32_kernel<16> (int32, one pair per CTA) for long pairs mixed with short ones",
@@ -65,7 +65,7 @@ KERNELS = {
 #: only reported when the file for THIS workload exists)
 NCU_FILES = {"c2": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"], "c3s": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"],
              "c3": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"], "c5w": ["r01_v4_duo_win_ncu_full.txt"],
-             "c2n": ["r02_general_ncu_full.txt", "r01_general_ncu_full.txt"]}
+             "c2n": ["r02_sets_ncu_full.txt"]}
 
 _SETS: dict = {}
 

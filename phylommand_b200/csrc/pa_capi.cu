@@ -67,6 +67,9 @@ struct Device {
     size_t cap_row_items = 0, cap_p2 = 0, cap_p4 = 0, cap_off2 = 0, cap_off4 = 0, cap_len = 0, cap_pure = 0, cap_bbuf = 0;
     uint8_t *fastok = nullptr;                // no gap character: the sequence can run on the s16x2 kernels
     size_t cap_fastok = 0;
+    uint32_t *order = nullptr;                // sequence indices, longest first (partners of an s16x2 work item: similar lengths)
+    uint4 *duo_items = nullptr;               // (a, b1, b2) work items of the chunk being launched (pa_duo_items_kernel)
+    size_t cap_order = 0, cap_duo_items = 0;
     int4 *bbuf = nullptr;
     uint32_t bbuf_rows = 0;
     uint32_t n_warps = 0;
@@ -154,6 +157,7 @@ struct Context {
     std::vector<unsigned long long> host_offsets;     // offsets into host_masks (n_seq + 1)
     std::vector<uint8_t> host_pure, host_fastok;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
+    std::vector<uint32_t> order;                 // sequence indices, longest first (stable)
     bool all_pure = true;
     bool all_fast = true;              // no sequence holds a gap character (everything can run on the s16x2 kernels)
     bool any_sparse = false;           // at least one gap-free sequence has IUPAC ambiguity codes (set form of the s16x2 kernel)
@@ -165,6 +169,7 @@ struct Context {
     uint32_t kduo_mask = DUO_KSET;     // PAIRALIGN_KDUO_SET: bit k set = width k allowed in the per-item choice (tuning)
     int kduo_step_cost = DUO_STEP_COST;          // PAIRALIGN_KDUO_A: per-step overhead of the cost model, in instructions (tuning)
     int duo_minb = 1;                  // PAIRALIGN_DUO_MINB=3: register-capped build of the s16x2 kernel, 3 CTAs per SM (tuning)
+    bool file_order = false;           // PAIRALIGN_ITEM_ORDER=file: partners of a work item are neighbours in file order (comparison)
     bool force_cta = false;            // PAIRALIGN_FORCE_CTA=1: every long pair takes a CTA regardless of how many there are
     uint64_t est_long_pairs = 0;       // pairs of the whole triangle with a sequence longer than LONG_LEN
     bool no_cta = false;               // PAIRALIGN_NO_CTA=1: long pairs stay on the one-pair-per-warp kernel (comparison)
@@ -179,7 +184,7 @@ void free_device(Device &d) {
     if (d.id < 0) return;
     cudaSetDevice(d.id);
     cudaFree(d.p2); cudaFree(d.p4); cudaFree(d.off2); cudaFree(d.off4); cudaFree(d.len); cudaFree(d.pure);
-    cudaFree(d.fastok);
+    cudaFree(d.fastok); cudaFree(d.order); cudaFree(d.duo_items);
     cudaFree(d.counters); cudaFree(d.n_deferred); cudaFree(d.deferred); cudaFree(d.deferred2); cudaFree(d.deferred3); cudaFree(d.bbuf);
     cudaFree(d.row_items); cudaFree(d.raw); cudaFree(d.raw_off);
     for (auto &c : d.ce) { for (auto &e : c.k) if (e) cudaEventDestroy(e); if (c.done) cudaEventDestroy(c.done); }
@@ -316,11 +321,21 @@ pa_pack_kernel(const uint8_t *raw, const unsigned long long *raw_off, const uint
     }
 }
 
-// item (pair of pairs) that holds triangle index q
-uint64_t item_of(const Context &c, uint64_t q) {
-    uint32_t a, b;
-    tri_pair(q, c.n_seq, a, b);
-    return c.row_items[a] + (uint64_t)(b - a - 1) / 2;
+// The s16x2 work items of the triangle range [first, first+count): rows a_lo..a_hi, the first from partner b_lo and the
+// last up to partner b_hi; every row contributes ceil(partners / 2) items (pa_duo_items_kernel fills them in).
+struct ItemRange { uint32_t a_lo, b_lo, a_hi, b_hi, items_first; uint64_t n_items; };
+ItemRange item_range(const Context &c, uint64_t first, uint64_t count) {
+    ItemRange r;
+    tri_pair(first, c.n_seq, r.a_lo, r.b_lo);
+    tri_pair(first + count - 1, c.n_seq, r.a_hi, r.b_hi);
+    if (r.a_lo == r.a_hi) {
+        r.items_first = (r.b_hi - r.b_lo + 2) / 2;
+        r.n_items = r.items_first;
+    } else {
+        r.items_first = (c.n_seq - r.b_lo + 1) / 2;
+        r.n_items = (uint64_t)r.items_first + (c.row_items[r.a_hi] - c.row_items[r.a_lo + 1]) + (r.b_hi - r.a_hi + 1) / 2;
+    }
+    return r;
 }
 
 // Launch the kernels for `count` elements (triangle range starting at `first`,
@@ -378,36 +393,48 @@ int launch_chunk(Context &c, Device &d, const pa_params &p, uint64_t first, uint
     PairSource src2 = src;
     const unsigned int *count2 = nullptr;
     if (duo) {
-        const uint64_t item_lo = item_of(c, first), item_hi = item_of(c, first + count - 1) + 1;
+        const ItemRange ir = item_range(c, first, count);
+        if (ir.n_items > d.cap_duo_items) {       // only ever grows (cudaFree waits for the chunk in flight)
+            cudaFree(d.duo_items); d.duo_items = nullptr; d.cap_duo_items = 0;
+            const size_t want = (size_t)std::max<uint64_t>(ir.n_items, std::min<uint64_t>(CHUNK_PAIRS, c.tri.pairs()) / 2 + c.n_seq + 2);
+            CU(cudaMalloc(&d.duo_items, want * sizeof(uint4)));
+            d.cap_duo_items = want;
+        }
+        pa_duo_items_kernel<<<(unsigned)std::min<uint32_t>(ir.a_hi - ir.a_lo + 1, 8u * (uint32_t)d.n_sm), 256, 0, d.stream>>>(
+            d.order, c.n_seq, ir.a_lo, ir.b_lo, ir.a_hi, ir.b_hi, d.row_items, ir.items_first, d.duo_items);
+        CU(cudaGetLastError());
+        d.launches += 1;
+        const uint4 *items = d.duo_items;
+        const uint64_t n_items = ir.n_items;
         if (c.kduo == 0 && p.gap_ext == -1)      // pairalign's own gap extension: the build with GE as an immediate
             pa_warp_duo_kernel<0, 1, -1><<<d.grid_duo_auto, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                S, sc, first, items, n_items, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, amb ? 1 : 0);
         else if (c.kduo == 0)
             pa_warp_duo_kernel<0><<<d.grid_duo_auto, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                S, sc, first, items, n_items, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred, c.kduo_mask, c.kduo_step_cost, win ? 1 : 0, amb ? 1 : 0);
         else if (c.kduo == 8)
             pa_warp_duo_kernel<8><<<d.grid_duo8, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                S, sc, first, items, n_items, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred);
         else if (c.duo_minb == 3)
             pa_warp_duo_kernel<KDUO, 3><<<d.grid_duo3, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                S, sc, first, items, n_items, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred);
         else
             pa_warp_duo_kernel<KDUO><<<d.grid_duo, threads, 0, d.stream>>>(
-                S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
+                S, sc, first, items, n_items, l16, d.counters, d.bbuf, d.bbuf_rows, d_out,
                 d.deferred, d.n_deferred);
         CU(cudaGetLastError());
         d.launches += 1;
         if (amb) {   // the items with an ambiguous sequence: same work items, 4-bit-set variant (its own work counter)
             if (p.gap_ext == -1 && p.match - p.mismatch == 12)
                 pa_warp_sets_kernel<-1, 12><<<d.grid_sets, threads, 0, d.stream>>>(
-                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
+                    S, sc, first, items, n_items, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
             else
                 pa_warp_sets_kernel<0><<<d.grid_sets, threads, 0, d.stream>>>(
-                    S, sc, first, count, d.row_items, item_lo, item_hi, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
+                    S, sc, first, items, n_items, l16, d.counters + 4, d.bbuf, d.bbuf_rows, d_out, win ? 1 : 0);
             CU(cudaGetLastError());
             d.launches += 1;
         }
@@ -684,6 +711,7 @@ int pa_init(const int *devices, int n_dev) {
     if (const char *f = std::getenv("PAIRALIGN_NO_AMB")) c->no_amb = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_DUO_MINB")) c->duo_minb = std::atoi(f);
     if (const char *f = std::getenv("PAIRALIGN_FORCE_CTA")) c->force_cta = (f[0] == '1');
+    if (const char *f = std::getenv("PAIRALIGN_ITEM_ORDER")) c->file_order = (f[0] == 'f');
     g_ctx = c;
     return PA_OK;
 }
@@ -776,6 +804,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     for (uint32_t s = 0; s <= n_seq; ++s) c.host_offsets[s] = offsets[s] - base0;
     c.row_items.assign((size_t)n_seq + 1, 0);
     for (uint32_t r = 0; r < n_seq; ++r) c.row_items[r + 1] = c.row_items[r] + ((uint64_t)(n_seq - 1 - r) + 1) / 2;
+    c.order.resize(n_seq);
+    for (uint32_t s = 0; s < n_seq; ++s) c.order[s] = s;
+    if (!c.file_order) std::stable_sort(c.order.begin(), c.order.end(), [&](uint32_t x, uint32_t y) { return len[x] > len[y]; });
 
     auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
         // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
@@ -798,6 +829,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         CU(grow((void **)&d.len, d.cap_len, nidx * 4));
         CU(grow((void **)&d.pure, d.cap_pure, nidx));
         CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
+        CU(grow((void **)&d.order, d.cap_order, nidx * 4));
         CU(grow((void **)&d.raw, d.cap_raw, (size_t)std::max<uint64_t>(n_bases, 16)));
         CU(grow((void **)&d.raw_off, d.cap_raw_off, (nidx + 1) * sizeof(unsigned long long)));
         d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
@@ -810,6 +842,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
             CU(cudaMemcpyAsync(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
             CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
             CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(cudaMemcpyAsync(d.order, c.order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
             pa_pack_kernel<<<(unsigned)std::min<uint32_t>(n_seq, 65535u * 16u), 128, 0, d.stream>>>(
                 d.raw, d.raw_off, d.len, d.off2, d.off4, n_seq, d.p2, d.p4, d.pure);
             CU(cudaGetLastError());
@@ -1116,22 +1149,31 @@ static int ops_range(Context &c, Device &d, const pa_params &prm, const uint32_t
             if (n_long == e0 - s0 && n_long_items % wave_items == 0) { ck_e0 = e0; ck_dbytes = dbytes; ck_obytes = obytes; }
         }
         const uint64_t nb = e0 - s0;
-        // work items of the s16x2 kernels: neighbouring entries with the same first sequence go together; an item with an
-        // ambiguous sequence runs on the set form
+        // work items of the s16x2 kernels: within a run of neighbouring entries with the same first sequence (and the same
+        // side of LONG_LEN) the entries go together in twos in order of the second sequence's length -- both pairs of an
+        // item sweep the passes of the longer one; an item with an ambiguous sequence runs on the set form
         for (auto &row : h_items) for (auto &v : row) v.clear();
-        for (uint64_t k = 0; k < nb; ++k) {
-            const uint32_t a = ia[s0 + k], b = ib[s0 + k];
-            int kl = klass(a, b);
-            if (!kl) continue;
-            const bool lng = std::max(c.len[a], c.len[b]) > LONG_LEN;
-            uint32_t second = 0xffffffffu;
-            if (k + 1 < nb) {
-                const uint32_t a2 = ia[s0 + k + 1], b2 = ib[s0 + k + 1];
-                const int kl2 = klass(a2, b2);
-                if (a2 == a && kl2 && (std::max(c.len[a], c.len[b2]) > LONG_LEN) == lng) { second = (uint32_t)(k + 1); kl = std::max(kl, kl2); }
+        std::vector<uint32_t> run;
+        for (uint64_t k = 0; k < nb;) {
+            const uint32_t a = ia[s0 + k];
+            if (!klass(a, ib[s0 + k])) { ++k; continue; }
+            const bool lng = std::max(c.len[a], c.len[ib[s0 + k]]) > LONG_LEN;
+            run.clear();
+            uint64_t k1 = k;
+            for (; k1 < nb && ia[s0 + k1] == a; ++k1) {
+                const uint32_t b = ib[s0 + k1];
+                if (!klass(a, b) || (std::max(c.len[a], c.len[b]) > LONG_LEN) != lng) break;
+                run.push_back((uint32_t)k1);
             }
-            h_items[lng ? 1 : 0][kl == 2 ? 1 : 0].push_back(make_uint2((uint32_t)k, second));
-            if (second != 0xffffffffu) ++k;
+            if (!c.file_order)
+                std::stable_sort(run.begin(), run.end(), [&](uint32_t x, uint32_t y) { return c.len[ib[s0 + x]] > c.len[ib[s0 + y]]; });
+            for (size_t j = 0; j < run.size(); j += 2) {
+                const bool two = j + 1 < run.size();
+                int kl = klass(a, ib[s0 + run[j]]);
+                if (two) kl = std::max(kl, klass(a, ib[s0 + run[j + 1]]));
+                h_items[lng ? 1 : 0][kl == 2 ? 1 : 0].push_back(make_uint2(run[j], two ? run[j + 1] : 0xffffffffu));
+            }
+            k = k1;
         }
         const size_t n_long_it = h_items[1][0].size() + h_items[1][1].size();
         const bool route_long = n_long_it && !c.no_cta && (c.force_cta || n_long_it < 4ull * (uint64_t)d.grid_moves_warp * WARPS_PER_CTA);

@@ -728,12 +728,49 @@ pa_warp_dp_kernel(const SeqStore S, const Scoring sc, const PairSource src, cons
     }
 }
 
-// Triangle range with pairs taken two at a time.  Work item u of row a covers the
-// pairs (a, a+1+2u) and (a, a+2+2u); row_item_start[a] = items in rows before a
-// (host-computed prefix, N+1 entries).  Items [item_lo, item_hi) are processed;
-// a pair is written only if its triangle index lies in [first, first+count).
-// Pairs the s16x2 path cannot take (a non-A/C/G/T sequence, or longer than
-// max_len16) are appended to `deferred` as range-relative indices.
+// Triangle range with pairs taken two at a time.  A work item is (a, b1, b2): the pairs (a, b1) and (a, b2) share
+// the row sequence a.  Both pairs sweep the passes of the LONGER column sequence (the shorter one's pad slots are
+// computed like real ones), so the two partners of an item should have about the same length: the partners b of a
+// row that lie in the range are taken in order of length (`order`: all sequence indices, longest first), two at a
+// time.  With neighbours in file order instead, a 400-900 bp set did 13 % more slots than it has cells.
+// pa_duo_items_kernel writes the items of one range (one CTA per row, block-wide compaction of `order`), item
+// `local_start(a) + j` = (a, j-th pair of partners); the DP kernels read items by index, results go to the pairs'
+// triangle indices.  Pairs the s16x2 path cannot take (a non-A/C/G/T sequence, or longer than max_len16) are
+// appended to `deferred` as range-relative indices.
+constexpr uint32_t NO_PARTNER = 0xffffffffu;
+__global__ void __launch_bounds__(256)
+pa_duo_items_kernel(const uint32_t *order, const uint32_t N, const uint32_t a_lo, const uint32_t b_lo, const uint32_t a_hi,
+                    const uint32_t b_hi, const unsigned long long *row_item_start, const uint32_t items_first, uint4 *items) {
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (uint32_t a = a_lo + blockIdx.x; a <= a_hi; a += gridDim.x) {
+        const uint32_t blo = (a == a_lo) ? b_lo : a + 1, bhi = (a == a_hi) ? b_hi : N - 1;
+        // items of the rows before a in this range: the first row may be partial, the others are whole rows
+        const unsigned long long base = (a == a_lo) ? 0ull : (unsigned long long)items_first + (row_item_start[a] - row_item_start[a_lo + 1]);
+        uint32_t running = 0;
+        for (uint32_t i0 = 0; i0 < N; i0 += 256) {
+            const uint32_t i = i0 + threadIdx.x;
+            const uint32_t idx = i < N ? order[i] : NO_PARTNER;
+            const bool keep = (idx != NO_PARTNER) && idx >= blo && idx <= bhi;
+            const uint32_t bal = __ballot_sync(FULL_MASK, keep);
+            if (lane == 0) warp_tot[wib] = __popc(bal);
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) { const uint32_t t = warp_tot[k]; if (k < wib) before += t; total += t; }
+            if (keep) {
+                const uint32_t pos = running + before + __popc(bal & ((1u << lane) - 1u));
+                uint32_t *it = reinterpret_cast<uint32_t *>(&items[base + (pos >> 1)]);
+                if (pos & 1u) it[2] = idx;
+                else { it[0] = a; it[1] = idx; }
+            }
+            running += total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && (running & 1u)) reinterpret_cast<uint32_t *>(&items[base + (running >> 1)])[2] = NO_PARTNER;
+    }
+}
+
 // Strip width (columns per lane) for a pair whose longer column sequence has m bases.  Column slots come in passes
 // of 32*K and the pad slots of the first pass are computed like real ones, so a fixed K wastes up to a whole pass
 // (m = 400 with K = 12: 768 slots).  Every pass has the same number of wavefront steps and a step costs about
@@ -758,8 +795,7 @@ __host__ __device__ __forceinline__ int duo_pick_k(const int m, const uint32_t k
 // GEC: compile-time gap extension (the host launches the GEC = -1 build for pairalign's own scoring), 0 = sc.ge.
 template <int K, int MINB = 1, int GEC = 0>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
-pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
-                   const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
+pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint4 *items, const uint64_t n_items,
                    const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
                    pa_pair_result *out, uint32_t *deferred, unsigned int *n_deferred,
                    const uint32_t kmask = DUO_KSET, const int step_cost = DUO_STEP_COST, const int win_ok = 0,
@@ -771,28 +807,21 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
     int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;     // bbuf_rows - 1 usable rows + the virtual-column row
     const uint32_t N = S.n_seq;
-    const uint64_t n_items = item_hi - item_lo;
 
     for (;;) {
         unsigned long long w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1ull);
         w = __shfl_sync(FULL_MASK, w, 0);
         if (w >= n_items) break;
-        const uint64_t item = item_lo + w;
-        // row a: last row with row_item_start[a] <= item
-        uint32_t lo = 0, hi = N - 1;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (row_item_start[mid] <= item) lo = mid; else hi = mid;
-        }
-        const uint32_t a = lo;
-        const uint32_t u = (uint32_t)(item - row_item_start[a]);
-        const uint32_t b1 = a + 1 + 2 * u;
-        uint32_t b2 = b1 + 1;
-        const uint64_t q1 = tri_row_start(a, N) + 2ull * u;
-        bool use1 = (q1 >= first && q1 < first + count);
-        bool use2 = (b2 < N) && (q1 + 1 >= first && q1 + 1 < first + count);
-        if (b2 >= N) b2 = b1;
+        const uint4 it = __ldg(&items[w]);
+        const uint32_t a = it.x, b1 = it.y;
+        uint32_t b2 = it.z;
+        const uint64_t q0 = tri_row_start(a, N) - a - 1;
+        const uint64_t q1 = q0 + b1;
+        bool use1 = true;
+        bool use2 = (b2 != NO_PARTNER);
+        if (!use2) b2 = b1;
+        const uint64_t q2 = q0 + b2;
         const int n = (int)S.len[a], m1 = (int)S.len[b1], m2 = (int)S.len[b2];
         // pairs this path cannot take go to the general / 32-bit kernels
         // longer than max_len16: floating-window variant (K = 0 kernel, when the host allows it), else deferred
@@ -806,7 +835,7 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         const bool ok2 = okx && good[b2] && m2 > 0 && (uint32_t)m2 <= lim;
         if (lane == 0) {
             if (use1 && !ok1) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 - first);
-            if (use2 && !ok2) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q1 + 1 - first);
+            if (use2 && !ok2) deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)(q2 - first);
         }
         use1 = use1 && ok1;
         use2 = use2 && ok2;
@@ -821,7 +850,7 @@ pa_warp_duo_kernel(const SeqStore S, const Scoring sc, const uint64_t first, con
         const uint32_t *ys1 = stage_seq(S.p2 + S.off2[y1], (uint32_t)(my1 + 15) >> 4, stage[wib][1], lane);
         const uint32_t *ys2 = stage_seq(S.p2 + S.off2[y2], (uint32_t)(my2 + 15) >> 4, stage[wib][2], lane);
         __syncwarp();
-        pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
+        pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q2 - first] : nullptr;
         // y1 / y2 / my1 / my2: what is actually aligned (a half that is not wanted mirrors the other one)
         const bool too_long = (uint32_t)n > max_len16 || (uint32_t)my1 > max_len16 || (uint32_t)my2 > max_len16;
         if constexpr (K == 0) {

@@ -302,8 +302,7 @@ __device__ __forceinline__ void align_warp_sets(const uint32_t *xs, const int n,
 // GEC / DC: compile-time gap extension / match - mismatch (the host launches <-1, 12> for pairalign's scoring), 0 = run time.
 template <int GEC = 0, int DC = 0>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint64_t count,
-                    const unsigned long long *row_item_start, const uint64_t item_lo, const uint64_t item_hi,
+pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, const uint4 *items, const uint64_t n_items,
                     const uint32_t max_len16, unsigned long long *work_counter, int4 *bbuf_all, const uint32_t bbuf_rows,
                     pa_pair_result *out, const int win_ok) {
     __shared__ __align__(16) uint32_t stage[WARPS_PER_CTA][3][STAGE_WORDS];
@@ -312,27 +311,21 @@ pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, co
     const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
     int4 *bbuf = bbuf_all + (size_t)gw * bbuf_rows;
     const uint32_t N = S.n_seq;
-    const uint64_t n_items = item_hi - item_lo;
 
     for (;;) {
         unsigned long long w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1ull);
         w = __shfl_sync(FULL_MASK, w, 0);
         if (w >= n_items) break;
-        const uint64_t item = item_lo + w;
-        uint32_t lo = 0, hi = N - 1;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (row_item_start[mid] <= item) lo = mid; else hi = mid;
-        }
-        const uint32_t a = lo;
-        const uint32_t u = (uint32_t)(item - row_item_start[a]);
-        const uint32_t b1 = a + 1 + 2 * u;
-        uint32_t b2 = b1 + 1;
-        const uint64_t q1 = tri_row_start(a, N) + 2ull * u;
-        bool use1 = (q1 >= first && q1 < first + count);
-        bool use2 = (b2 < N) && (q1 + 1 >= first && q1 + 1 < first + count);
-        if (b2 >= N) b2 = b1;
+        const uint4 it = __ldg(&items[w]);
+        const uint32_t a = it.x, b1 = it.y;
+        uint32_t b2 = it.z;
+        const uint64_t q0 = tri_row_start(a, N) - a - 1;
+        const uint64_t q1 = q0 + b1;
+        bool use1 = true;
+        bool use2 = (b2 != NO_PARTNER);
+        if (!use2) b2 = b1;
+        const uint64_t q2 = q0 + b2;
         const int n = (int)S.len[a], m1 = (int)S.len[b1], m2 = (int)S.len[b2];
         const uint32_t lim = win_ok ? 0xffffffffu : max_len16;
         const bool okx = S.fastok[a] && n > 0 && (uint32_t)n <= lim;
@@ -347,7 +340,7 @@ pa_warp_sets_kernel(const SeqStore S, const Scoring sc, const uint64_t first, co
         const uint32_t *ys1 = stage_seq(S.p4 + S.off4[y1], (uint32_t)(my1 + 7) >> 3, stage[wib][1], lane);
         const uint32_t *ys2 = stage_seq(S.p4 + S.off4[y2], (uint32_t)(my2 + 7) >> 3, stage[wib][2], lane);
         __syncwarp();
-        pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q1 + 1 - first] : nullptr;
+        pa_pair_result *r1 = use1 ? &out[q1 - first] : nullptr, *r2 = use2 ? &out[q2 - first] : nullptr;
         const bool too_long = (uint32_t)n > max_len16 || (uint32_t)my1 > max_len16 || (uint32_t)my2 > max_len16;
         if (too_long) align_warp_sets<12, true, GEC, DC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 2, r1, r2, lane);
         else align_warp_sets<12, false, GEC, DC>(xs, n, ys1, my1, ys2, my2, sc, bbuf, bbuf_rows - 1, r1, r2, lane);
