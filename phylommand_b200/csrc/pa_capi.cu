@@ -8,12 +8,14 @@
 #include "pa_peak.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -98,6 +100,7 @@ struct Device {
     } ce[2];
     cudaEvent_t ev[6] = {};                       // pa_align_pairs_ops, pair-list upload
     double cta_ms = 0;
+    uint64_t gen = 0;                             // Context::upload_gen of the sequence set this device holds
     // timing accumulators of the last call
     double duo_ms = 0, fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
     uint32_t launches = 0;
@@ -158,6 +161,18 @@ struct Context {
     std::vector<uint8_t> host_pure, host_fastok;
     std::vector<unsigned long long> row_items;   // pairs-of-pairs work items in rows before r
     std::vector<uint32_t> order;                 // sequence indices, longest first (stable)
+    // geometry of the packed set (what a device needs, beside the members above, to take the set over: upload_device_*)
+    std::vector<uint32_t> off2, off4;
+    uint64_t n_bases = 0;
+    size_t words2 = 4, words4 = 4;
+    uint64_t upload_gen = 0;                     // counts pa_upload_sequences calls; a device is current when Device::gen matches
+    // Devices come up on their own host threads (pa_init_async returns when the first one is ready): 0 coming up, 1 ready,
+    // 2 failed.  A ready device's entry in `dev` is complete and only touched under g_mu from then on.
+    std::unique_ptr<std::atomic<int>[]> dev_state;
+    std::vector<std::string> dev_err;
+    std::vector<std::thread> bringup;
+    std::atomic<int> occ_ready{0};               // 1: occ holds the occupancies asked on the first device, 2: that failed
+    struct Occ { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_warp_sets, moves_cta, fast, cta, gen, stats; } occ = {};
     bool all_pure = true;
     bool all_fast = true;              // no sequence holds a gap character (everything can run on the s16x2 kernels)
     bool any_sparse = false;           // at least one gap-free sequence has IUPAC ambiguity codes (set form of the s16x2 kernel)
@@ -589,9 +604,111 @@ extern "C" {
 int pa_api_version(void) { return PA_API_VERSION; }
 const char *pa_last_error(void) { return g_err.c_str(); }
 
-int pa_init(const int *devices, int n_dev) {
+// Tear a context down: its bring-up threads first (they write into c->dev), then the devices.
+static void destroy_context(Context *c) {
+    if (!c) return;
+    for (auto &t : c->bringup) if (t.joinable()) t.join();
+    for (auto &d : c->dev) free_device(d);
+    if (c->host_masks) cudaFreeHost(c->host_masks);
+    delete c;
+}
+
+// Resident CTAs per SM of every kernel: asked once, on the first device (the query makes the driver load the kernel for that
+// device, a few hundred milliseconds for the whole module; the devices of a context are the same chip).
+static cudaError_t query_occupancy(Context::Occ &o) {
+    int occ = 0, occ_c = 0;
+    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
+    o.duo = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO, 3>, WARPS_PER_CTA * 32, 0);
+    o.duo3 = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
+    o.duo8 = std::max(1, occ);
+    // the two builds of a kernel (gap extension at run time / as an immediate) share one grid size: the smaller
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
+    o.duo_auto = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1, 12>, WARPS_PER_CTA * 32, 0);
+    o.sets = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
+    o.moves_warp = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0, true, 0>, WARPS_PER_CTA * 32, 0);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1, true, 12>, WARPS_PER_CTA * 32, 0);
+    o.moves_warp_sets = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
+    o.moves_cta = std::max(1, std::min(occ, occ_c));
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
+    o.fast = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
+    o.cta = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
+    o.gen = std::max(1, occ);
+    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
+    o.stats = std::max(1, occ);
+    return e2;
+}
+
+// One device from nothing to ready, on the calling thread: primary context (most of a second: the driver creates them one
+// after the other whatever the number of host threads), attributes, the occupancy table (first device only; the others
+// wait for it), streams, events and scratch.  Ends by publishing the device's state.
+static void bring_up_device(Context *c, size_t k) {
+    Device &d = c->dev[k];
+    char msg[256] = "";
+    auto done = [&](bool ok) {
+        if (!ok) c->dev_err[k] = msg;
+        if (k == 0) c->occ_ready.store(ok ? 1 : 2, std::memory_order_release);
+        c->dev_state[k].store(ok ? 1 : 2, std::memory_order_release);
+    };
+    int major = 0, minor = 0, n_sm = 0;
+    cudaError_t e = cudaSetDevice(d.id);
+    if (e == cudaSuccess) e = cudaFree(nullptr);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d.id);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, d.id);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d.id);
+    if (e != cudaSuccess) { snprintf(msg, sizeof msg, "cannot select device %d: %s", d.id, cudaGetErrorString(e)); done(false); return; }
+    if (major < 10) { snprintf(msg, sizeof msg, "device %d is sm_%d%d; this module is built for sm_100a only", d.id, major, minor); done(false); return; }
+    d.n_sm = n_sm;
+    if (k == 0) {
+        e = query_occupancy(c->occ);
+        if (e != cudaSuccess) { snprintf(msg, sizeof msg, "occupancy query failed: %s", cudaGetErrorString(e)); done(false); return; }
+        c->occ_ready.store(1, std::memory_order_release);
+    } else {
+        int st;
+        while ((st = c->occ_ready.load(std::memory_order_acquire)) == 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        if (st != 1) { snprintf(msg, sizeof msg, "device %d given up: the first device failed", d.id); done(false); return; }
+    }
+    const Context::Occ &o = c->occ;
+    e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
+    for (auto &ev : d.ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto &ce : d.ce) {
+        for (auto &ev : ce.k) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+        if (e == cudaSuccess) e = cudaEventCreate(&ce.done);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&d.counters, 5 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
+    d.grid_duo = o.duo * d.n_sm; d.grid_duo3 = o.duo3 * d.n_sm; d.grid_duo8 = o.duo8 * d.n_sm;
+    d.grid_duo_auto = o.duo_auto * d.n_sm; d.grid_sets = o.sets * d.n_sm;
+    d.grid_moves_warp = o.moves_warp * d.n_sm; d.grid_moves_warp_sets = o.moves_warp_sets * d.n_sm; d.grid_moves_cta = o.moves_cta * d.n_sm;
+    d.grid_fast = o.fast * d.n_sm; d.grid_cta = o.cta * d.n_sm; d.grid_gen = o.gen * d.n_sm; d.grid_stats = o.stats * d.n_sm;
+    d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, std::max(d.grid_moves_warp, d.grid_moves_warp_sets)), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
+    if (e != cudaSuccess) { snprintf(msg, sizeof msg, "device %d setup failed: %s", d.id, cudaGetErrorString(e)); done(false); return; }
+    done(true);
+}
+
+// wait for every device of the context; the first failure is reported
+static int wait_devices_locked(Context &c) {
+    for (auto &t : c.bringup) if (t.joinable()) t.join();
+    for (size_t k = 0; k < c.dev.size(); ++k)
+        if (c.dev_state[k].load(std::memory_order_acquire) != 1) return fail(PA_ECUDA, "%s", c.dev_err[k].c_str());
+    return PA_OK;
+}
+
+static int init_impl(const int *devices, int n_dev, bool async) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx) { for (auto &d : g_ctx->dev) free_device(d); if (g_ctx->host_masks) cudaFreeHost(g_ctx->host_masks); delete g_ctx; g_ctx = nullptr; }
+    if (g_ctx) { destroy_context(g_ctx); g_ctx = nullptr; }
     int avail = 0;
     cudaError_t e = cudaGetDeviceCount(&avail);
     if (e != cudaSuccess || avail <= 0)
@@ -602,105 +719,24 @@ int pa_init(const int *devices, int n_dev) {
     else for (int k = 0; k < n_dev; ++k) ids.push_back(devices[k]);
     for (int id : ids)
         if (id < 0 || id >= avail) return fail(PA_EINVAL, "device %d out of range (0..%d)", id, avail - 1);
-    if (ids.size() > 1) {
-        // Primary contexts take most of a second each; create them side by side, one host thread per device
-        // (errors surface again in the sequential set-up below).
-        std::vector<std::thread> th;
-        for (int id : ids) th.emplace_back([id] { if (cudaSetDevice(id) == cudaSuccess) cudaFree(nullptr); });
-        for (auto &t : th) t.join();
-    }
     Context *c = new Context();
-    for (int id : ids) {
-        Device d;
-        d.id = id;
-        int major = 0, minor = 0, n_sm = 0;
-        if (cudaSetDevice(id) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, id) != cudaSuccess ||
-            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, id) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, id) != cudaSuccess) {
-            delete c; return fail(PA_ECUDA, "cannot select device %d", id);
-        }
-        if (major < 10) { delete c; return fail(PA_ENODEVICE, "device %d is sm_%d%d; this module is built for sm_100a only", id, major, minor); }
-        d.n_sm = n_sm;
-        c->dev.push_back(d);
+    c->dev.resize(ids.size());
+    for (size_t k = 0; k < ids.size(); ++k) c->dev[k].id = ids[k];
+    c->dev_state.reset(new std::atomic<int>[ids.size()]);
+    for (size_t k = 0; k < ids.size(); ++k) c->dev_state[k].store(0);
+    c->dev_err.assign(ids.size(), std::string());
+    // the other devices start coming up while the first one is set up on this thread
+    for (size_t k = 1; k < ids.size(); ++k) c->bringup.emplace_back(bring_up_device, c, k);
+    bring_up_device(c, 0);
+    if (c->dev_state[0].load(std::memory_order_acquire) != 1) {
+        const std::string msg = c->dev_err[0];
+        const bool wrong_chip = msg.find("sm_100a only") != std::string::npos;
+        destroy_context(c);
+        return fail(wrong_chip ? PA_ENODEVICE : PA_ECUDA, "%s", msg.c_str());
     }
-    struct { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_warp_sets, moves_cta, fast, cta, gen, stats; } occ0 = {};
-    {
-    int occ = 0;
-    cudaError_t e2 = cudaSetDevice(c->dev[0].id);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO>, WARPS_PER_CTA * 32, 0);
-    occ0.duo = std::max(1, occ);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<KDUO, 3>, WARPS_PER_CTA * 32, 0);
-    occ0.duo3 = std::max(1, occ);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<8>, WARPS_PER_CTA * 32, 0);
-    occ0.duo8 = std::max(1, occ);
-    // the two builds of a kernel (gap extension at run time / as an immediate) share one grid size: the smaller
-    int occ_c = 0;
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_kernel<0>, WARPS_PER_CTA * 32, 0);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_kernel<0, 1, -1>, WARPS_PER_CTA * 32, 0);
-    occ0.duo_auto = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_sets_kernel<0>, WARPS_PER_CTA * 32, 0);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_sets_kernel<-1, 12>, WARPS_PER_CTA * 32, 0);
-    occ0.sets = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0>, WARPS_PER_CTA * 32, 0);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1>, WARPS_PER_CTA * 32, 0);
-    occ0.moves_warp = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_duo_moves_kernel<0, true, 0>, WARPS_PER_CTA * 32, 0);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_warp_duo_moves_kernel<-1, true, 12>, WARPS_PER_CTA * 32, 0);
-    occ0.moves_warp_sets = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta_duo_moves_kernel<0>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pa_cta_duo_moves_kernel<-1>, MOVES_CTA_WARPS * 32, moves_cta_smem(false));
-    occ0.moves_cta = std::max(1, std::min(occ, occ_c));
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp32_kernel<KFAST>, WARPS_PER_CTA * 32, 0);
-    occ0.fast = std::max(1, occ);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_cta32_kernel<KFAST>, CTA_WARPS * 32, 0);
-    occ0.cta = std::max(1, occ);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_warp_dp_kernel<KGEN, true>, WARPS_PER_CTA * 32, 0);
-    occ0.gen = std::max(1, occ);
-    if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_aligned_stats_kernel, WARPS_PER_CTA * 32, 0);
-    occ0.stats = std::max(1, occ);
-    if (e2 != cudaSuccess) {
-        std::string msg = cudaGetErrorString(e2);
-        delete c;
-        return fail(PA_ECUDA, "occupancy query failed: %s", msg.c_str());
-    }
-    }
-    // Streams, events and scratch: every device sets itself up on its own host thread.
-    std::vector<cudaError_t> setup_err(c->dev.size(), cudaSuccess);
-    auto setup = [&](size_t k) {
-        Device &d = c->dev[k];
-        cudaSetDevice(d.id);
-        cudaError_t e2 = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
-        for (auto &ev : d.ev) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
-        for (auto &ce : d.ce) {
-            for (auto &ev : ce.k) if (e2 == cudaSuccess) e2 = cudaEventCreate(&ev);
-            if (e2 == cudaSuccess) e2 = cudaEventCreate(&ce.done);
-        }
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.counters, 5 * sizeof(unsigned long long));
-        if (e2 == cudaSuccess) e2 = cudaMalloc(&d.n_deferred, 3 * sizeof(unsigned int));
-        // resident CTAs per SM of every kernel: asked once, on the first device (the query makes the driver load the kernel
-        // for that device, a few hundred milliseconds for the whole module; the devices of a context are the same chip)
-        d.grid_duo = occ0.duo * d.n_sm; d.grid_duo3 = occ0.duo3 * d.n_sm; d.grid_duo8 = occ0.duo8 * d.n_sm;
-        d.grid_duo_auto = occ0.duo_auto * d.n_sm; d.grid_sets = occ0.sets * d.n_sm;
-        d.grid_moves_warp = occ0.moves_warp * d.n_sm; d.grid_moves_warp_sets = occ0.moves_warp_sets * d.n_sm; d.grid_moves_cta = occ0.moves_cta * d.n_sm;
-        d.grid_fast = occ0.fast * d.n_sm; d.grid_cta = occ0.cta * d.n_sm; d.grid_gen = occ0.gen * d.n_sm; d.grid_stats = occ0.stats * d.n_sm;
-        d.n_warps = (uint32_t)std::max(std::max(std::max(std::max(std::max(std::max(d.grid_duo, d.grid_sets), d.grid_duo_auto), d.grid_duo3), d.grid_duo8), std::max(std::max(d.grid_fast, std::max(d.grid_moves_warp, d.grid_moves_warp_sets)), d.grid_gen)) * WARPS_PER_CTA, std::max(d.grid_cta, d.grid_moves_cta));
-        setup_err[k] = e2;
-    };
-    if (c->dev.size() == 1) setup(0);
-    else {
-        std::vector<std::thread> th;
-        for (size_t k = 0; k < c->dev.size(); ++k) th.emplace_back(setup, k);
-        for (auto &t : th) t.join();
-    }
-    for (size_t k = 0; k < c->dev.size(); ++k) {
-        if (setup_err[k] != cudaSuccess) {
-            std::string msg = cudaGetErrorString(setup_err[k]);
-            const int bad = c->dev[k].id;
-            for (auto &dd : c->dev) free_device(dd);
-            delete c;
-            return fail(PA_ECUDA, "device %d setup failed: %s", bad, msg.c_str());
-        }
+    if (!async) {
+        const int rc = wait_devices_locked(*c);
+        if (rc) { const std::string msg = g_err; destroy_context(c); return fail(rc, "%s", msg.c_str()); }
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
@@ -716,12 +752,26 @@ int pa_init(const int *devices, int n_dev) {
     return PA_OK;
 }
 
+int pa_init(const int *devices, int n_dev) { return init_impl(devices, n_dev, false); }
+int pa_init_async(const int *devices, int n_dev) { return init_impl(devices, n_dev, true); }
+
+int pa_wait_devices(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
+    return wait_devices_locked(*g_ctx);
+}
+
+int pa_devices_ready(void) {
+    if (!g_ctx) return 0;
+    int n = 0;
+    for (size_t k = 0; k < g_ctx->dev.size(); ++k) n += g_ctx->dev_state[k].load(std::memory_order_acquire) == 1 ? 1 : 0;
+    return n;
+}
+
 void pa_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx) return;
-    for (auto &d : g_ctx->dev) free_device(d);
-    if (g_ctx->host_masks) cudaFreeHost(g_ctx->host_masks);
-    delete g_ctx;
+    destroy_context(g_ctx);
     g_ctx = nullptr;
 }
 
@@ -770,6 +820,81 @@ size_t pa_encode_sequence(const char *text, size_t len, uint8_t *out, size_t *n_
     return n;
 }
 
+// A device takes over the current sequence set from the host's copies in the context: raw sets + geometry, packing on the
+// device (pa_pack_kernel); all asynchronous on d.stream.  upload_device_end adds what the host scan produced and waits.
+static int upload_device_begin(Context &c, Device &d) {
+    auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
+        // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
+        if (bytes <= cap && *ptr) return cudaSuccess;
+        cudaFree(*ptr);
+        *ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(ptr, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    };
+    const uint32_t n_seq = c.n_seq;
+    const size_t nidx = std::max<size_t>(n_seq, 1);
+    CU(cudaSetDevice(d.id));
+    CU(grow((void **)&d.row_items, d.cap_row_items, c.row_items.size() * sizeof(unsigned long long)));
+    CU(grow((void **)&d.p2, d.cap_p2, c.words2 * 4));
+    CU(grow((void **)&d.p4, d.cap_p4, c.words4 * 4));
+    CU(grow((void **)&d.off2, d.cap_off2, nidx * 4));
+    CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
+    CU(grow((void **)&d.len, d.cap_len, nidx * 4));
+    CU(grow((void **)&d.pure, d.cap_pure, nidx));
+    CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
+    CU(grow((void **)&d.order, d.cap_order, nidx * 4));
+    CU(grow((void **)&d.raw, d.cap_raw, (size_t)std::max<uint64_t>(c.n_bases, 16)));
+    CU(grow((void **)&d.raw_off, d.cap_raw_off, (nidx + 1) * sizeof(unsigned long long)));
+    d.bbuf_rows = std::max<uint32_t>(c.max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
+    if (c.max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
+    CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
+    CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+    if (n_seq) {
+        if (c.n_bases) CU(cudaMemcpyAsync(d.raw, c.host_masks, (size_t)c.n_bases, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.raw_off, c.host_offsets.data(), ((size_t)n_seq + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.off2, c.off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.off4, c.off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.len, c.len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.order, c.order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+        pa_pack_kernel<<<(unsigned)std::min<uint32_t>(n_seq, 65535u * 16u), 128, 0, d.stream>>>(
+            d.raw, d.raw_off, d.len, d.off2, d.off4, n_seq, d.p2, d.p4, d.pure);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemsetAsync(d.p2, 0, 16, d.stream));
+        CU(cudaMemsetAsync(d.p4, 0, 16, d.stream));
+    }
+    return PA_OK;
+}
+
+static int upload_device_end(Context &c, Device &d) {
+    CU(cudaSetDevice(d.id));
+    // d.pure was written by pa_pack_kernel from the same bytes; the host's copy is what launch decisions use
+    if (c.n_seq) CU(cudaMemcpyAsync(d.fastok, c.host_fastok.data(), (size_t)c.n_seq, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    d.gen = c.upload_gen;
+    return PA_OK;
+}
+
+// a device that came up after the last pa_upload_sequences (pa_init_async) catches up before its first batch
+static int ensure_uploaded(Context &c, Device &d) {
+    if (d.gen == c.upload_gen) return PA_OK;
+    int rc = upload_device_begin(c, d);
+    if (rc) return rc;
+    return upload_device_end(c, d);
+}
+
+// The devices that are ready now (device 0 always is); a device that failed to come up fails the call.
+static int active_devices(Context &c, std::vector<size_t> &act) {
+    act.clear();
+    for (size_t k = 0; k < c.dev.size(); ++k) {
+        const int st = c.dev_state[k].load(std::memory_order_acquire);
+        if (st == 1) act.push_back(k);
+        else if (st == 2) return fail(PA_ECUDA, "%s", c.dev_err[k].c_str());
+    }
+    return PA_OK;
+}
+
 int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t n_seq) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
@@ -791,11 +916,15 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     }
     const uint64_t n_bases = n_seq ? offsets[n_seq] - offsets[0] : 0;
     const uint64_t base0 = n_seq ? offsets[0] : 0;
+    std::vector<size_t> act;
+    int rc = active_devices(c, act);
+    if (rc) return rc;
     // The host keeps the sets (pa_align_pair_traceback rebuilds strings from them) in pinned memory, which is also
     // where the devices fetch them from.  Packing is the devices' job (pa_pack_kernel): the host only scans.
     if (n_bases > c.host_masks_cap) {
         if (c.host_masks) cudaFreeHost(c.host_masks);
         c.host_masks = nullptr; c.host_masks_cap = 0;
+        CU(cudaSetDevice(c.dev[0].id));
         CU(cudaMallocHost(&c.host_masks, (size_t)std::max<uint64_t>(n_bases, 4096)));
         c.host_masks_cap = std::max<uint64_t>(n_bases, 4096);
     }
@@ -807,49 +936,17 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.order.resize(n_seq);
     for (uint32_t s = 0; s < n_seq; ++s) c.order[s] = s;
     if (!c.file_order) std::stable_sort(c.order.begin(), c.order.end(), [&](uint32_t x, uint32_t y) { return len[x] > len[y]; });
-
-    auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
-        // device buffers only grow: re-uploading a set of the same size costs copies, not allocations
-        if (bytes <= cap && *ptr) return cudaSuccess;
-        cudaFree(*ptr);
-        *ptr = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(ptr, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    };
-    const size_t nidx = std::max<size_t>(n_seq, 1);
-    const size_t words2 = (size_t)std::max<uint64_t>(w2, 4), words4 = (size_t)std::max<uint64_t>(w4, 4);
-    for (auto &d : c.dev) {         // raw sets + geometry to every device, packing there; all asynchronous
-        CU(cudaSetDevice(d.id));
-        CU(grow((void **)&d.row_items, d.cap_row_items, c.row_items.size() * sizeof(unsigned long long)));
-        CU(grow((void **)&d.p2, d.cap_p2, words2 * 4));
-        CU(grow((void **)&d.p4, d.cap_p4, words4 * 4));
-        CU(grow((void **)&d.off2, d.cap_off2, nidx * 4));
-        CU(grow((void **)&d.off4, d.cap_off4, nidx * 4));
-        CU(grow((void **)&d.len, d.cap_len, nidx * 4));
-        CU(grow((void **)&d.pure, d.cap_pure, nidx));
-        CU(grow((void **)&d.fastok, d.cap_fastok, nidx));
-        CU(grow((void **)&d.order, d.cap_order, nidx * 4));
-        CU(grow((void **)&d.raw, d.cap_raw, (size_t)std::max<uint64_t>(n_bases, 16)));
-        CU(grow((void **)&d.raw_off, d.cap_raw_off, (nidx + 1) * sizeof(unsigned long long)));
-        d.bbuf_rows = std::max<uint32_t>(max_len, 1) + 1;   // + the virtual-column row of the s16x2 kernel
-        if (max_len > 4096) d.bbuf_rows *= 2;               // floating-window s16x2 variant: (values, offsets) per row
-        CU(grow((void **)&d.bbuf, d.cap_bbuf, (size_t)d.n_warps * d.bbuf_rows * sizeof(int4)));
-        CU(cudaMemcpyAsync(d.row_items, c.row_items.data(), c.row_items.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
-        if (n_seq) {
-            if (n_bases) CU(cudaMemcpyAsync(d.raw, c.host_masks, (size_t)n_bases, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.raw_off, c.host_offsets.data(), ((size_t)n_seq + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.off2, off2.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.off4, off4.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.len, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            CU(cudaMemcpyAsync(d.order, c.order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, d.stream));
-            pa_pack_kernel<<<(unsigned)std::min<uint32_t>(n_seq, 65535u * 16u), 128, 0, d.stream>>>(
-                d.raw, d.raw_off, d.len, d.off2, d.off4, n_seq, d.p2, d.p4, d.pure);
-            CU(cudaGetLastError());
-        } else {
-            CU(cudaMemsetAsync(d.p2, 0, 16, d.stream));
-            CU(cudaMemsetAsync(d.p4, 0, 16, d.stream));
-        }
+    c.n_seq = n_seq;
+    c.len = len;
+    c.off2 = off2; c.off4 = off4;
+    c.n_bases = n_bases;
+    c.words2 = (size_t)std::max<uint64_t>(w2, 4); c.words4 = (size_t)std::max<uint64_t>(w4, 4);
+    c.max_len = max_len;
+    c.min_len = n_seq ? *std::min_element(len.begin(), len.end()) : 0;
+    ++c.upload_gen;
+    for (size_t k : act) {         // devices that are up; one that comes up later catches up before its first batch
+        rc = upload_device_begin(c, c.dev[k]);
+        if (rc) return rc;
     }
 
     // Meanwhile on the host: which sequences are plain A/C/G/T and which of the others are free of gap characters
@@ -879,12 +976,8 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         fastok[s] = ok ? 1 : 0;
         all_fast = all_fast && ok;
     }
-    c.n_seq = n_seq;
     c.host_pure = pure;
     c.host_fastok = fastok;
-    c.len = len;
-    c.max_len = max_len;
-    c.min_len = n_seq ? *std::min_element(len.begin(), len.end()) : 0;
     c.all_pure = all_pure;
     c.all_fast = all_fast;
     c.any_sparse = any_sparse;
@@ -896,16 +989,9 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
         c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
     }
-    for (auto &d : c.dev) {
-        CU(cudaSetDevice(d.id));
-        if (n_seq) {
-            // d.pure was written by pa_pack_kernel from the same bytes; the host's copy is what launch decisions use
-            CU(cudaMemcpyAsync(d.fastok, fastok.data(), (size_t)n_seq, cudaMemcpyHostToDevice, d.stream));
-        }
-    }
-    for (auto &d : c.dev) {       // the host vectors above die at return
-        CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.stream));
+    for (size_t k : act) {
+        rc = upload_device_end(c, c.dev[k]);
+        if (rc) return rc;
     }
     return PA_OK;
 }
@@ -988,7 +1074,12 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
             if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
     }
     const auto t0 = std::chrono::steady_clock::now();
-    const size_t nd = d_resident ? 1 : c.dev.size();
+    // the devices that are up now share the call (pa_init_async: the others join with a later batch)
+    std::vector<size_t> act;
+    rc = active_devices(c, act);
+    if (rc) return rc;
+    if (d_resident) act.resize(1);
+    const size_t nd = act.size();
     std::vector<uint64_t> bounds(nd + 1);
     if (!ia) {
         if (nd == 1) { bounds[0] = first; bounds[1] = first + count; }
@@ -1004,8 +1095,10 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     std::vector<double> kms(2 * nd, 0.0);
     auto work = [&](size_t p) {
         const uint64_t lo = bounds[p], n = bounds[p + 1] - bounds[p];
+        Device &d = c.dev[act[p]];
+        rcs[p] = ensure_uploaded(c, d);
+        if (rcs[p]) { errs[p] = g_err; return; }
         if (via_moves) {
-            Device &d = c.dev[p];
             d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
             d.launches = 0;
             std::vector<uint32_t> la((size_t)n), lb((size_t)n);
@@ -1015,8 +1108,8 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
             rcs[p] = ops_range(c, d, *params, la.data(), lb.data(), 0, n, nullptr, nullptr, nullptr, out ? out + (lo - first) : nullptr,
                                &kms[2 * p], d_resident);
         }
-        else if (!ia) rcs[p] = run_range(c, c.dev[p], *params, lo, n, nullptr, nullptr, out ? out + (lo - first) : nullptr, d_resident);
-        else rcs[p] = run_range(c, c.dev[p], *params, 0, n, ia + lo, ib + lo, out + lo, nullptr);
+        else if (!ia) rcs[p] = run_range(c, d, *params, lo, n, nullptr, nullptr, out ? out + (lo - first) : nullptr, d_resident);
+        else rcs[p] = run_range(c, d, *params, 0, n, ia + lo, ib + lo, out + lo, nullptr);
         if (rcs[p]) errs[p] = g_err;
     };
     if (nd == 1) work(0);
@@ -1030,7 +1123,7 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     pa_timing &tm = c.timing;
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
-        const Device &d = c.dev[p];
+        const Device &d = c.dev[act[p]];
         tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.cta_ms + d.gen_ms + kms[2 * p + 1]);
         tm.walk_ms = std::max(tm.walk_ms, kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
@@ -1325,7 +1418,12 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     // contiguous ranges of the list with nearly equal DP cells, one per device (each on its own host thread);
     // every range writes its own slice of ops / n_ops / res, so nothing is shared
     const auto t0 = std::chrono::steady_clock::now();
-    const size_t nd = c.dev.size();
+    std::vector<size_t> act;            // the devices that are up now (pa_init_async: the others join with a later batch)
+    {
+        const int rc_act = active_devices(c, act);
+        if (rc_act) return rc_act;
+    }
+    const size_t nd = act.size();
     std::vector<uint64_t> bounds(nd + 1, count);
     bounds[0] = 0;
     if (nd > 1) {
@@ -1339,9 +1437,11 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     std::vector<int> rcs(nd, PA_OK);
     std::vector<std::string> errs(nd);
     std::vector<double> kms(2 * nd, 0.0);
-    for (auto &d : c.dev) { d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
+    for (size_t k : act) { Device &d = c.dev[k]; d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
     auto work = [&](size_t p) {
-        rcs[p] = ops_range(c, c.dev[p], *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p], nullptr);
+        Device &d = c.dev[act[p]];
+        rcs[p] = ensure_uploaded(c, d);
+        if (!rcs[p]) rcs[p] = ops_range(c, d, *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p], nullptr);
         if (rcs[p]) errs[p] = g_err;
     };
     if (nd == 1) work(0);
@@ -1355,7 +1455,7 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     pa_timing &tm = c.timing;
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
-        const Device &d = c.dev[p];
+        const Device &d = c.dev[act[p]];
         tm.kernel_ms = std::max(tm.kernel_ms, kms[2 * p] + kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
         tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);

@@ -414,28 +414,33 @@ std::string lookup_taxonomy(const std::map<std::string, std::string> &tax, const
     return std::string();
 }
 
-// Double-buffered batches: the CUDA module fills one buffer while the caller replays the other.
-template <class Produce, class Consume>
-void pipeline(uint64_t total, uint64_t chunk, Produce produce, Consume consume) {
+// Double-buffered batches: the CUDA module fills one buffer while the caller replays the other.  chunk_at(first) is the
+// size of the batch that starts at `first`; produce and consume are told which of the two buffers (slot) a batch uses.
+template <class ChunkAt, class Produce, class Consume>
+void pipeline(uint64_t total, ChunkAt chunk_at, Produce produce, Consume consume) {
     if (total == 0) return;
     std::vector<pa_pair_result> buf[2];
     std::string error;
-    auto fill = [&](int slot, uint64_t first) {
-        const uint64_t n = std::min<uint64_t>(chunk, total - first);
+    auto fill = [&](int slot, uint64_t first, uint64_t n) {
         buf[slot].resize((size_t)n);
-        try { produce(first, n, buf[slot].data()); } catch (const std::exception &e) { error = e.what(); }
+        try { produce(first, n, buf[slot].data(), slot); } catch (const std::exception &e) { error = e.what(); }
     };
+    auto size_at = [&](uint64_t first) { return std::min<uint64_t>(std::max<uint64_t>(1, chunk_at(first)), total - first); };
     int slot = 0;
-    fill(0, 0);
-    for (uint64_t first = 0; first < total; first += chunk) {
+    uint64_t n = size_at(0);
+    fill(0, 0, n);
+    for (uint64_t first = 0; first < total;) {
         if (!error.empty()) throw std::runtime_error(error);
-        const uint64_t next = first + chunk;
+        const uint64_t next = first + n;
+        const uint64_t n_next = next < total ? size_at(next) : 0;
         std::thread worker;
-        if (next < total) worker = std::thread(fill, slot ^ 1, next);
+        if (n_next) worker = std::thread(fill, slot ^ 1, next, n_next);
         // a throwing consumer must not leave the worker joinable (its destructor would call std::terminate)
-        try { consume(first, buf[slot]); } catch (...) { if (worker.joinable()) worker.join(); throw; }
+        try { consume(first, buf[slot], slot); } catch (...) { if (worker.joinable()) worker.join(); throw; }
         if (worker.joinable()) worker.join();
         slot ^= 1;
+        first = next;
+        n = n_next;
     }
 }
 
@@ -521,6 +526,11 @@ void run_fasta(const Options &opt, Out &out) {
             const uint64_t op_bytes = (256ull << 20) * (uint64_t)std::max(1, pa_device_count());
             const uint64_t chunk_pairs = want_ops ? std::max<uint64_t>(1, std::min<uint64_t>(kChunkPairs, op_bytes / (2ull * max_len)))
                                                   : kChunkPairs;
+            // while devices are still coming up (pa_init_async) the batches are an eighth of the size, so that a device
+            // that has just arrived does not wait long for its first share
+            auto chunk_at = [&](uint64_t) {
+                return pa_devices_ready() < pa_device_count() ? std::max<uint64_t>(1, chunk_pairs / 8) : chunk_pairs;
+            };
             size_t cur_k = 0;
             int cur_slot = 0;
             if (want_ops)
@@ -535,8 +545,8 @@ void run_fasta(const Options &opt, Out &out) {
             // pairs one thread's 0.3 GB/s of formatting was five times slower than the alignments it prints
             const bool bulk_text = want_ops && opt.quiet && !opt.matrix && !batch.any_unknown();   // '-m -a': rows are framed per pair
             std::string bulk;
-            auto consume_bulk = [&](uint64_t first, size_t n) {
-                const SeqpairBatch::OpBatch &ob = opb[(first / chunk_pairs) & 1];
+            auto consume_bulk = [&](uint64_t first, size_t n, int slot) {
+                const SeqpairBatch::OpBatch &ob = opb[slot];
                 std::vector<uint32_t> pa_(n), pb_(n);
                 std::vector<uint64_t> at(n + 1, 0);
                 uint32_t ca = 0, cb = 0;
@@ -578,9 +588,9 @@ void run_fasta(const Options &opt, Out &out) {
                 }
                 out.raw(bulk.data(), bulk.size());
             };
-            auto consume = [&](uint64_t first, const std::vector<pa_pair_result> &recs) {
-                cur_slot = (int)((first / chunk_pairs) & 1);
-                if (bulk_text) { consume_bulk(first, recs.size()); return; }
+            auto consume = [&](uint64_t first, const std::vector<pa_pair_result> &recs, int slot) {
+                cur_slot = slot;
+                if (bulk_text) { consume_bulk(first, recs.size(), slot); return; }
                 for (size_t k = 0; k < recs.size(); ++k) {
                     cur_k = k;
                     if (b == 0) { a = 0; b = 1; }
@@ -590,7 +600,7 @@ void run_fasta(const Options &opt, Out &out) {
                     if (++b == N) { ++a; b = a + 1; }
                 }
             };
-            auto produce = [&](uint64_t first, uint64_t n, pa_pair_result *dst) {
+            auto produce = [&](uint64_t first, uint64_t n, pa_pair_result *dst, int slot) {
                 if (need_stats) batch.align_range(params, first, n, dst);
                 else std::memset(dst, 0, (size_t)n * sizeof(pa_pair_result));
                 if (want_ops) {
@@ -601,7 +611,7 @@ void run_fasta(const Options &opt, Out &out) {
                         ia_b[(size_t)k] = pa; ib_b[(size_t)k] = pb;
                         if (++pb == N) { ++pa; pb = pa + 1; }
                     }
-                    batch.alignments(params, ia_b, ib_b, opb[(first / chunk_pairs) & 1]);
+                    batch.alignments(params, ia_b, ib_b, opb[slot]);
                 }
             };
             double replay_ms = 0, produce_ms = 0;       // busy time of the two sides of the pipeline (PAIRALIGN_TIMING)
@@ -610,9 +620,9 @@ void run_fasta(const Options &opt, Out &out) {
                 fn();
                 acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             };
-            pipeline(total, chunk_pairs,
-                     [&](uint64_t first, uint64_t n, pa_pair_result *dst) { timed(produce_ms, [&] { produce(first, n, dst); }); },
-                     [&](uint64_t first, const std::vector<pa_pair_result> &recs) { timed(replay_ms, [&] { consume(first, recs); }); });
+            pipeline(total, chunk_at,
+                     [&](uint64_t first, uint64_t n, pa_pair_result *dst, int slot) { timed(produce_ms, [&] { produce(first, n, dst, slot); }); },
+                     [&](uint64_t first, const std::vector<pa_pair_result> &recs, int slot) { timed(replay_ms, [&] { consume(first, recs, slot); }); });
             if (timer.on)
                 std::cerr << "[pairalign_b200] pipeline busy: align " << produce_ms << " ms, replay + print " << replay_ms << " ms" << std::endl;
             if (timer.on) {

@@ -278,6 +278,47 @@ def test_sub_ranges_and_pair_lists(gpu, oracle):
         gpu.align_pairs([0], [25])
 
 
+def test_devices_that_come_up_later_join_in(gpu, oracle):
+    """pa_init_async: the first call may run on one device while the second is still coming up; once it is there it takes
+    the sequence set over by itself and shares the work.  Same records either way, for ranges, lists and op strings.
+    On a one-GPU box the second device entry is the same chip (the code path is the same)."""
+    import torch
+    second = 1 if torch.cuda.device_count() >= 2 else 0
+    _, seqs = synth.make_random(40, 23, 50, 900)
+    _, amb = synth.make_random(4, 24, 50, 600, iupac=0.02)
+    enc = [synth.to_masks(s) for s in seqs] + [gpu.encode("N" + synth.to_text(s)) for s in amb]
+    want = _oracle_all(oracle, enc)
+    try:
+        gpu.init([0, second], wait=False)
+        gpu.upload(enc)                               # the second device may or may not have seen this upload
+        _same(gpu.align_all_pairs(), want)
+        gpu.wait_devices()
+        assert gpu.devices_ready() == 2
+        _same(gpu.align_all_pairs(), want)
+        assert gpu.timing()["n_devices"] == 2
+        _same(gpu.align_all_pairs(100, 300), want[100:400])
+        ia, ib = np.array([0, 5, 41, 7, 3, 20, 11]), np.array([9, 2, 6, 40, 30, 21, 12])
+        stats = gpu.align_pairs(ia, ib)
+        for k in range(len(ia)):
+            assert tuple(stats[k]) == tuple(oracle.align_forward(enc[ia[k]], enc[ib[k]]))
+        lens = np.array([len(e) for e in enc])
+        ops, off, n_ops, res = gpu.align_pairs_ops(ia, ib, lens)
+        assert res.tobytes() == stats.tobytes()
+        for k in range(len(ia)):
+            r, wx, wy = oracle.align_full(enc[ia[k]], enc[ib[k]])
+            ax, ay = _render(ops[int(off[k]):int(off[k]) + int(n_ops[k])], enc[ia[k]], enc[ib[k]])
+            assert ax == wx.tolist() and ay == wy.tolist()
+        # a second set uploaded while both are up, then a fresh asynchronous start that is waited for first
+        gpu.upload(enc[:20])
+        _same(gpu.align_all_pairs(), _oracle_all(oracle, enc[:20]))
+        gpu.init([0, second], wait=False)
+        gpu.wait_devices()
+        gpu.upload(enc)
+        _same(gpu.align_all_pairs(), want)
+    finally:
+        gpu.init()                                    # the session's one-device context for the tests that follow
+
+
 def test_aligned_mode(gpu, oracle):
     """pairalign -A: position-wise over min(n,m) columns, gaps and IUPAC included."""
     _, seqs = synth.make_random(20, 31, 1, 300, iupac=0.05, gaps=0.2)
