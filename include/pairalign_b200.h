@@ -91,17 +91,8 @@ typedef struct {
 /* Create the process-wide context on the given CUDA devices (devices==NULL or
  * n_dev<=0: device 0 only).  Calling it again re-initialises. */
 int pa_init(const int *devices, int n_dev);
-/* The same, but returns as soon as the FIRST device is ready; the others come up on
- * background threads (a CUDA context takes most of a second and the driver creates them
- * one after the other).  Every compute call shares its work among the devices that are
- * ready when it starts, so the batches of a long run spread over more devices as they
- * arrive; results do not depend on how many took part.  A device that fails to come up
- * fails the next call.  pa_wait_devices blocks until all are ready. */
-int pa_init_async(const int *devices, int n_dev);
-int pa_wait_devices(void);
-int pa_devices_ready(void);         /* devices of the context that are ready now */
 void pa_shutdown(void);
-int pa_device_count(void);          /* devices in the context, ready or coming up (0 if none) */
+int pa_device_count(void);          /* devices in the context (0 if none)      */
 int pa_visible_devices(void);       /* CUDA devices this process can see (0 if none) */
 int pa_api_version(void);
 const char *pa_last_error(void);

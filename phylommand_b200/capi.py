@@ -39,9 +39,6 @@ class PaTiming(C.Structure):
 #: every symbol include/pairalign_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pa_init": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
-    "pa_init_async": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
-    "pa_wait_devices": (C.c_int, []),
-    "pa_devices_ready": (C.c_int, []),
     "pa_shutdown": (None, []),
     "pa_device_count": (C.c_int, []),
     "pa_visible_devices": (C.c_int, []),
@@ -115,23 +112,13 @@ def make_params(**kw) -> PaParams:
     return PaParams(**d)
 
 
-def init(devices=None, wait: bool = True) -> None:
-    """wait=False: pa_init_async (returns when the first device is ready, the others join later calls as they come up)."""
+def init(devices=None) -> None:
     lib = load()
-    fn = lib.pa_init if wait else lib.pa_init_async
     if devices is None:
-        _check(fn(None, 0))
+        _check(lib.pa_init(None, 0))
     else:
         arr = (C.c_int * len(devices))(*devices)
-        _check(fn(arr, len(devices)))
-
-
-def wait_devices() -> None:
-    _check(load().pa_wait_devices())
-
-
-def devices_ready() -> int:
-    return int(load().pa_devices_ready())
+        _check(lib.pa_init(arr, len(devices)))
 
 
 def shutdown() -> None:

@@ -100,7 +100,6 @@ struct Device {
     } ce[2];
     cudaEvent_t ev[6] = {};                       // pa_align_pairs_ops, pair-list upload
     double cta_ms = 0;
-    uint64_t gen = 0;                             // Context::upload_gen of the sequence set this device holds
     // timing accumulators of the last call
     double duo_ms = 0, fast_ms = 0, gen_ms = 0, d2h_ms = 0, h2d_ms = 0;
     uint32_t launches = 0;
@@ -165,9 +164,7 @@ struct Context {
     std::vector<uint32_t> off2, off4;
     uint64_t n_bases = 0;
     size_t words2 = 4, words4 = 4;
-    uint64_t upload_gen = 0;                     // counts pa_upload_sequences calls; a device is current when Device::gen matches
-    // Devices come up on their own host threads (pa_init_async returns when the first one is ready): 0 coming up, 1 ready,
-    // 2 failed.  A ready device's entry in `dev` is complete and only touched under g_mu from then on.
+    // pa_init brings the devices up on one host thread each: 0 coming up, 1 ready, 2 failed (with its message)
     std::unique_ptr<std::atomic<int>[]> dev_state;
     std::vector<std::string> dev_err;
     std::vector<std::thread> bringup;
@@ -698,15 +695,7 @@ static void bring_up_device(Context *c, size_t k) {
     done(true);
 }
 
-// wait for every device of the context; the first failure is reported
-static int wait_devices_locked(Context &c) {
-    for (auto &t : c.bringup) if (t.joinable()) t.join();
-    for (size_t k = 0; k < c.dev.size(); ++k)
-        if (c.dev_state[k].load(std::memory_order_acquire) != 1) return fail(PA_ECUDA, "%s", c.dev_err[k].c_str());
-    return PA_OK;
-}
-
-static int init_impl(const int *devices, int n_dev, bool async) {
+int pa_init(const int *devices, int n_dev) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ctx) { destroy_context(g_ctx); g_ctx = nullptr; }
     int avail = 0;
@@ -725,18 +714,18 @@ static int init_impl(const int *devices, int n_dev, bool async) {
     c->dev_state.reset(new std::atomic<int>[ids.size()]);
     for (size_t k = 0; k < ids.size(); ++k) c->dev_state[k].store(0);
     c->dev_err.assign(ids.size(), std::string());
-    // the other devices start coming up while the first one is set up on this thread
+    // Every device on its own host thread, side by side.  Measured on an 8-GPU box (profiles/r02_cli_init_8gpu.txt): the
+    // first CUDA call of the process costs ~5 s there whatever follows, a context 0.1-0.4 s; bringing the other devices
+    // up in the background while the first one already computes (tried) has nothing to overlap.
     for (size_t k = 1; k < ids.size(); ++k) c->bringup.emplace_back(bring_up_device, c, k);
     bring_up_device(c, 0);
-    if (c->dev_state[0].load(std::memory_order_acquire) != 1) {
-        const std::string msg = c->dev_err[0];
+    for (auto &t : c->bringup) if (t.joinable()) t.join();
+    for (size_t k = 0; k < ids.size(); ++k) {
+        if (c->dev_state[k].load(std::memory_order_acquire) == 1) continue;
+        const std::string msg = c->dev_err[k];
         const bool wrong_chip = msg.find("sm_100a only") != std::string::npos;
         destroy_context(c);
         return fail(wrong_chip ? PA_ENODEVICE : PA_ECUDA, "%s", msg.c_str());
-    }
-    if (!async) {
-        const int rc = wait_devices_locked(*c);
-        if (rc) { const std::string msg = g_err; destroy_context(c); return fail(rc, "%s", msg.c_str()); }
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
@@ -750,22 +739,6 @@ static int init_impl(const int *devices, int n_dev, bool async) {
     if (const char *f = std::getenv("PAIRALIGN_ITEM_ORDER")) c->file_order = (f[0] == 'f');
     g_ctx = c;
     return PA_OK;
-}
-
-int pa_init(const int *devices, int n_dev) { return init_impl(devices, n_dev, false); }
-int pa_init_async(const int *devices, int n_dev) { return init_impl(devices, n_dev, true); }
-
-int pa_wait_devices(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx) return fail(PA_ENODEVICE, "pa_init() has not succeeded");
-    return wait_devices_locked(*g_ctx);
-}
-
-int pa_devices_ready(void) {
-    if (!g_ctx) return 0;
-    int n = 0;
-    for (size_t k = 0; k < g_ctx->dev.size(); ++k) n += g_ctx->dev_state[k].load(std::memory_order_acquire) == 1 ? 1 : 0;
-    return n;
 }
 
 void pa_shutdown(void) {
@@ -820,7 +793,7 @@ size_t pa_encode_sequence(const char *text, size_t len, uint8_t *out, size_t *n_
     return n;
 }
 
-// A device takes over the current sequence set from the host's copies in the context: raw sets + geometry, packing on the
+// One device's copy of the current sequence set, from the host's copies in the context: raw sets + geometry, packing on the
 // device (pa_pack_kernel); all asynchronous on d.stream.  upload_device_end adds what the host scan produced and waits.
 static int upload_device_begin(Context &c, Device &d) {
     auto grow = [](void **ptr, size_t &cap, size_t bytes) -> cudaError_t {
@@ -872,26 +845,6 @@ static int upload_device_end(Context &c, Device &d) {
     // d.pure was written by pa_pack_kernel from the same bytes; the host's copy is what launch decisions use
     if (c.n_seq) CU(cudaMemcpyAsync(d.fastok, c.host_fastok.data(), (size_t)c.n_seq, cudaMemcpyHostToDevice, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    d.gen = c.upload_gen;
-    return PA_OK;
-}
-
-// a device that came up after the last pa_upload_sequences (pa_init_async) catches up before its first batch
-static int ensure_uploaded(Context &c, Device &d) {
-    if (d.gen == c.upload_gen) return PA_OK;
-    int rc = upload_device_begin(c, d);
-    if (rc) return rc;
-    return upload_device_end(c, d);
-}
-
-// The devices that are ready now (device 0 always is); a device that failed to come up fails the call.
-static int active_devices(Context &c, std::vector<size_t> &act) {
-    act.clear();
-    for (size_t k = 0; k < c.dev.size(); ++k) {
-        const int st = c.dev_state[k].load(std::memory_order_acquire);
-        if (st == 1) act.push_back(k);
-        else if (st == 2) return fail(PA_ECUDA, "%s", c.dev_err[k].c_str());
-    }
     return PA_OK;
 }
 
@@ -916,9 +869,7 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     }
     const uint64_t n_bases = n_seq ? offsets[n_seq] - offsets[0] : 0;
     const uint64_t base0 = n_seq ? offsets[0] : 0;
-    std::vector<size_t> act;
-    int rc = active_devices(c, act);
-    if (rc) return rc;
+    int rc;
     // The host keeps the sets (pa_align_pair_traceback rebuilds strings from them) in pinned memory, which is also
     // where the devices fetch them from.  Packing is the devices' job (pa_pack_kernel): the host only scans.
     if (n_bases > c.host_masks_cap) {
@@ -943,9 +894,8 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
     c.words2 = (size_t)std::max<uint64_t>(w2, 4); c.words4 = (size_t)std::max<uint64_t>(w4, 4);
     c.max_len = max_len;
     c.min_len = n_seq ? *std::min_element(len.begin(), len.end()) : 0;
-    ++c.upload_gen;
-    for (size_t k : act) {         // devices that are up; one that comes up later catches up before its first batch
-        rc = upload_device_begin(c, c.dev[k]);
+    for (auto &d : c.dev) {
+        rc = upload_device_begin(c, d);
         if (rc) return rc;
     }
 
@@ -989,8 +939,8 @@ int pa_upload_sequences(const uint8_t *masks, const uint64_t *offsets, uint32_t 
         for (uint32_t s = 0; s < n_seq; ++s) n_long += len[s] > LONG_LEN ? 1 : 0;
         c.est_long_pairs = n_seq ? n_long * (uint64_t)(n_seq - 1) - n_long * (n_long ? n_long - 1 : 0) / 2 : 0;
     }
-    for (size_t k : act) {
-        rc = upload_device_end(c, c.dev[k]);
+    for (auto &d : c.dev) {
+        rc = upload_device_end(c, d);
         if (rc) return rc;
     }
     return PA_OK;
@@ -1074,12 +1024,7 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
             if (ia[k] >= c.n_seq || ib[k] >= c.n_seq) return fail(PA_ERANGE, "pair %llu names a sequence out of range", (unsigned long long)k);
     }
     const auto t0 = std::chrono::steady_clock::now();
-    // the devices that are up now share the call (pa_init_async: the others join with a later batch)
-    std::vector<size_t> act;
-    rc = active_devices(c, act);
-    if (rc) return rc;
-    if (d_resident) act.resize(1);
-    const size_t nd = act.size();
+    const size_t nd = d_resident ? 1 : c.dev.size();
     std::vector<uint64_t> bounds(nd + 1);
     if (!ia) {
         if (nd == 1) { bounds[0] = first; bounds[1] = first + count; }
@@ -1095,9 +1040,7 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     std::vector<double> kms(2 * nd, 0.0);
     auto work = [&](size_t p) {
         const uint64_t lo = bounds[p], n = bounds[p + 1] - bounds[p];
-        Device &d = c.dev[act[p]];
-        rcs[p] = ensure_uploaded(c, d);
-        if (rcs[p]) { errs[p] = g_err; return; }
+        Device &d = c.dev[p];
         if (via_moves) {
             d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0;
             d.launches = 0;
@@ -1123,7 +1066,7 @@ static int align_impl(const pa_params *params, uint64_t first, uint64_t count, c
     pa_timing &tm = c.timing;
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
-        const Device &d = c.dev[act[p]];
+        const Device &d = c.dev[p];
         tm.kernel_ms = std::max(tm.kernel_ms, d.duo_ms + d.fast_ms + d.cta_ms + d.gen_ms + kms[2 * p + 1]);
         tm.walk_ms = std::max(tm.walk_ms, kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
@@ -1418,12 +1361,7 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     // contiguous ranges of the list with nearly equal DP cells, one per device (each on its own host thread);
     // every range writes its own slice of ops / n_ops / res, so nothing is shared
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<size_t> act;            // the devices that are up now (pa_init_async: the others join with a later batch)
-    {
-        const int rc_act = active_devices(c, act);
-        if (rc_act) return rc_act;
-    }
-    const size_t nd = act.size();
+    const size_t nd = c.dev.size();
     std::vector<uint64_t> bounds(nd + 1, count);
     bounds[0] = 0;
     if (nd > 1) {
@@ -1437,11 +1375,10 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     std::vector<int> rcs(nd, PA_OK);
     std::vector<std::string> errs(nd);
     std::vector<double> kms(2 * nd, 0.0);
-    for (size_t k : act) { Device &d = c.dev[k]; d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
+    for (auto &d : c.dev) { d.duo_ms = d.fast_ms = d.cta_ms = d.gen_ms = d.d2h_ms = d.h2d_ms = 0; d.launches = 0; }
     auto work = [&](size_t p) {
-        Device &d = c.dev[act[p]];
-        rcs[p] = ensure_uploaded(c, d);
-        if (!rcs[p]) rcs[p] = ops_range(c, d, *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p], nullptr);
+        Device &d = c.dev[p];
+        rcs[p] = ops_range(c, d, *params, ia, ib, bounds[p], bounds[p + 1], ops, op_offsets, n_ops, res, &kms[2 * p], nullptr);
         if (rcs[p]) errs[p] = g_err;
     };
     if (nd == 1) work(0);
@@ -1455,7 +1392,7 @@ static int ops_impl(const pa_params *params, const uint32_t *ia, const uint32_t 
     pa_timing &tm = c.timing;
     tm = pa_timing();
     for (size_t p = 0; p < nd; ++p) {
-        const Device &d = c.dev[act[p]];
+        const Device &d = c.dev[p];
         tm.kernel_ms = std::max(tm.kernel_ms, kms[2 * p] + kms[2 * p + 1]);
         tm.dp_cta_ms = std::max(tm.dp_cta_ms, d.cta_ms);
         tm.dp_duo_ms = std::max(tm.dp_duo_ms, d.duo_ms);

@@ -526,11 +526,7 @@ void run_fasta(const Options &opt, Out &out) {
             const uint64_t op_bytes = (256ull << 20) * (uint64_t)std::max(1, pa_device_count());
             const uint64_t chunk_pairs = want_ops ? std::max<uint64_t>(1, std::min<uint64_t>(kChunkPairs, op_bytes / (2ull * max_len)))
                                                   : kChunkPairs;
-            // while devices are still coming up (pa_init_async) the batches are an eighth of the size, so that a device
-            // that has just arrived does not wait long for its first share
-            auto chunk_at = [&](uint64_t) {
-                return pa_devices_ready() < pa_device_count() ? std::max<uint64_t>(1, chunk_pairs / 8) : chunk_pairs;
-            };
+            auto chunk_at = [&](uint64_t) { return chunk_pairs; };
             size_t cur_k = 0;
             int cur_slot = 0;
             if (want_ops)

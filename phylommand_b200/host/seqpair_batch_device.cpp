@@ -29,13 +29,7 @@ void init_devices(double est_cells) {
         }
         for (int k = 0; k < n; ++k) ids.push_back(k);
     }
-    // several devices: start on the first one that is ready, the others join later batches as their contexts come up
-    // (PAIRALIGN_INIT=sync waits for all of them first)
-    const char *mode = std::getenv("PAIRALIGN_INIT");
-    if (ids.size() > 1 && !(mode && mode[0] == 's'))
-        check(pa_init_async(ids.data(), (int)ids.size()), "pa_init_async");
-    else
-        check(pa_init(ids.empty() ? nullptr : ids.data(), (int)ids.size()), "pa_init");
+    check(pa_init(ids.empty() ? nullptr : ids.data(), (int)ids.size()), "pa_init");
 }
 
 void SeqpairBatch::upload() {

@@ -33,7 +33,6 @@ void pair_of(uint64_t k, uint32_t n_seq, uint32_t *a, uint32_t *b) {      // row
 
 extern "C" {
 int pa_device_count(void) { return 1; }
-int pa_devices_ready(void) { return 1; }
 int pa_get_timing(pa_timing *) { return PA_ENODEVICE; }
 void pa_shutdown(void) {}
 int pa_pair_from_index(uint64_t k, uint32_t *a, uint32_t *b) {

@@ -79,18 +79,14 @@ def test_cli_argument_errors(exe, workdir):
     assert r.returncode == 1 and b"Do not recognize argument 'nonsense'" in r.stderr
 
 
-@pytest.mark.parametrize("init", ["async", "sync"])
-def test_cli_two_devices_same_output(exe, workdir, init):
-    """The in-process multi-device path (one host thread, stream set and pinned buffer per device entry), with the
-    devices coming up in the background (pa_init_async, the command line's default) and all up front.  On a box with one
-    GPU the second entry is the same chip: the code path is the same."""
+def test_cli_two_devices_same_output(exe, workdir):
+    """The in-process multi-device path (one host thread, stream set and pinned buffer per device entry).  On a box with
+    one GPU the second entry is the same chip: the code path is the same."""
     import os
     import torch
     devices = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
-    env = dict(os.environ, PAIRALIGN_DEVICES=devices, PAIRALIGN_INIT=init)
+    env = dict(os.environ, PAIRALIGN_DEVICES=devices)
     for flags, golden in ((["-j", "-n", "-m"], "pure_j_n_m.out"), (["-a", "-n"], "pure_a_n.out")):
-        if not (CLI_DIR / golden).exists():
-            continue
         want = (CLI_DIR / golden).read_bytes()
         r = subprocess.run([str(exe), *flags, "pure.fst"], cwd=workdir, capture_output=True, timeout=600, env=env)
         assert r.returncode == 0 and r.stdout == want, (flags, r.stderr[-500:])

@@ -278,10 +278,10 @@ def test_sub_ranges_and_pair_lists(gpu, oracle):
         gpu.align_pairs([0], [25])
 
 
-def test_devices_that_come_up_later_join_in(gpu, oracle):
-    """pa_init_async: the first call may run on one device while the second is still coming up; once it is there it takes
-    the sequence set over by itself and shares the work.  Same records either way, for ranges, lists and op strings.
-    On a one-GPU box the second device entry is the same chip (the code path is the same)."""
+def test_two_device_entries_share_a_call(gpu, oracle):
+    """The in-process multi-device path at the C-ABI: every device entry takes a cell-balanced share of a range, of a
+    pair list and of a batch of alignments; the records are those of one device.  On a one-GPU box the second entry
+    is the same chip (the code path is the same)."""
     import torch
     second = 1 if torch.cuda.device_count() >= 2 else 0
     _, seqs = synth.make_random(40, 23, 50, 900)
@@ -289,11 +289,8 @@ def test_devices_that_come_up_later_join_in(gpu, oracle):
     enc = [synth.to_masks(s) for s in seqs] + [gpu.encode("N" + synth.to_text(s)) for s in amb]
     want = _oracle_all(oracle, enc)
     try:
-        gpu.init([0, second], wait=False)
-        gpu.upload(enc)                               # the second device may or may not have seen this upload
-        _same(gpu.align_all_pairs(), want)
-        gpu.wait_devices()
-        assert gpu.devices_ready() == 2
+        gpu.init([0, second])
+        gpu.upload(enc)
         _same(gpu.align_all_pairs(), want)
         assert gpu.timing()["n_devices"] == 2
         _same(gpu.align_all_pairs(100, 300), want[100:400])
@@ -308,13 +305,8 @@ def test_devices_that_come_up_later_join_in(gpu, oracle):
             r, wx, wy = oracle.align_full(enc[ia[k]], enc[ib[k]])
             ax, ay = _render(ops[int(off[k]):int(off[k]) + int(n_ops[k])], enc[ia[k]], enc[ib[k]])
             assert ax == wx.tolist() and ay == wy.tolist()
-        # a second set uploaded while both are up, then a fresh asynchronous start that is waited for first
-        gpu.upload(enc[:20])
+        gpu.upload(enc[:20])                          # a second, smaller set on both
         _same(gpu.align_all_pairs(), _oracle_all(oracle, enc[:20]))
-        gpu.init([0, second], wait=False)
-        gpu.wait_devices()
-        gpu.upload(enc)
-        _same(gpu.align_all_pairs(), want)
     finally:
         gpu.init()                                    # the session's one-device context for the tests that follow
 
