@@ -441,6 +441,7 @@ __device__ __forceinline__ void duo_row(const uint32_t (&Hs)[K], uint32_t (&Hd)[
 // +-WIN_T.  The recurrence itself is untouched: it only ever combines values of one frame.  The edge rows handed to
 // the next pass carry their offsets in a second int4 (bbuf rows 2i, 2i+1), maxima are compared as true 32-bit values.
 constexpr int WIN_T = 8192, WIN_Q = 4096;
+constexpr int WIN_PREFETCH = 8;      // steps between the L2 prefetch of an edge row and its use (a step is ~1 us of the warp)
 constexpr int WIN_BIAS = -16384;     // centre of the window in stored terms: values stay in about [-29000, -3800]
 
 template <int K, bool WIN = false, int GEC = 0>
@@ -546,6 +547,9 @@ __device__ __forceinline__ void align_warp_duo(const uint32_t *xs, const int n, 
             if (WIN) {
                 fOA = __ldcg(&feed[fmul * min(2 * t + 2, n - 1) + 1]);
                 fOB = __ldcg(&feed[fmul * min(2 * t + 3, n - 1) + 1]);
+                // the edge rows of a 30 kb pass (0.9 MB per warp, 1.1 GB per grid) left L2 long before the next pass
+                // reads them: fetch the line WIN_PREFETCH steps ahead into L2 so that the loads above find it there
+                if (p > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(&feed[2 * min(2 * t + 2 + 2 * WIN_PREFETCH, n - 1)]));
             }
             const uint32_t xi2 = (xw >> ((iA & 15) * 2)) & 15u;
             xw = xs[min(max(iA + 2, 0) >> 4, x_last_word)];
