@@ -466,7 +466,8 @@ def main() -> None:
              "e2e": {"value": r["total_pairs"] / r["el_e2e"], "ms_per_step": 1e3 * r["el_e2e"],
                      "gcups": r["total_cells"] / r["el_e2e"] / 1e9},
              "parity_spot_check_all_ranks": r["ok"],
-             "cells_per_rank": {"min": min(r["cells_rank"]), "max": max(r["cells_rank"])}}
+             "cells_per_rank": {"min": min(r["cells_rank"]), "max": max(r["cells_rank"])},
+             "kernel_ms_per_rank": {"min": min(r["kern_rank"]), "max": max(r["kern_rank"])}}
         if peak is not None:
             rf = roofline_of(r, name)
             e["roofline"] = {k: rf[k] for k in ("achieved", "peak", "frac", "kernel", "kernel_ms_per_step", "kernel_gcups_per_gpu")}
