@@ -273,15 +273,32 @@ __global__ void __launch_bounds__(32) nj_sums(const SumArgs g, const __grid_cons
         }
     };
     for (int t = 0; t < NJ_STAGES - 1; ++t) issue(t);
+    // The adds of a column are one dependent chain (4 cycles each); a tile's 64 values are therefore fetched into
+    // registers while the PREVIOUS tile is being added, so that no shared-memory latency sits between two adds
+    // (16 loads, then 16 adds, per trip of the old loop: 7.2 cycles per row; now the chain alone).
+    float v[TR], w[TR];
+    mbar_wait(&full[0], 0u);
+    {
+        const float *col = tile + lane;
+#pragma unroll
+        for (int a = 0; a < TR; ++a) v[a] = col[a * W];
+    }
     float s = 0.0f;
     for (int t = 0; t < n_tiles; ++t) {
-        issue(t + NJ_STAGES - 1);               // refills the slot every lane finished with in the last iteration
-        const int st = t % NJ_STAGES;
-        mbar_wait(&full[st], (unsigned int)(t / NJ_STAGES) & 1u);
-        const float *col = tile + st * NJ_TILE + lane;
-#pragma unroll 16
-        for (int a = 0; a < TR; ++a) s = __fadd_rn(s, col[a * W]);
-        __syncwarp();
+        __syncwarp();                           // every lane has tile t in registers: its slot's predecessor may be refilled
+        issue(t + NJ_STAGES - 1);               // into the slot of tile t - 1
+        if (t + 1 < n_tiles) {
+            const int st = (t + 1) % NJ_STAGES;
+            mbar_wait(&full[st], (unsigned int)((t + 1) / NJ_STAGES) & 1u);
+            const float *col = tile + st * NJ_TILE + lane;
+#pragma unroll
+            for (int a = 0; a < TR; ++a) { s = __fadd_rn(s, v[a]); w[a] = col[a * W]; }
+#pragma unroll
+            for (int a = 0; a < TR; ++a) v[a] = w[a];
+        } else {
+#pragma unroll
+            for (int a = 0; a < TR; ++a) s = __fadd_rn(s, v[a]);
+        }
     }
     g.S2[b] = dead_b ? neg_inf() : s;           // columns past P are dead: -inf
 }
