@@ -159,7 +159,15 @@ public:
         buf_.append(tmp, (size_t)format(v, tmp));
         maybe_flush();
     }
-    void raw(const char *p, size_t n) { buf_.append(p, n); maybe_flush(); }
+    void raw(const char *p, size_t n) {
+        if (n >= (1u << 20)) {      // a batch of rendered alignments (up to gigabytes): straight to stdout, no second copy
+            if (!buf_.empty()) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); }
+            std::fwrite(p, 1, n, stdout);
+            return;
+        }
+        buf_.append(p, n);
+        maybe_flush();
+    }
     void fill(char c, size_t n) { buf_.append(n, c); maybe_flush(); }
     void flush() {
         if (!buf_.empty()) { std::fwrite(buf_.data(), 1, buf_.size(), stdout); buf_.clear(); }
