@@ -73,6 +73,19 @@ def test_host_side_matches_reference(exe, workdir, entry):
         made.unlink()
 
 
+def test_bulk_rendering_of_a_large_batch(exe, tmp_path):
+    """pairalign -a -n with more than a megabyte of text in one batch: the batch is rendered into one buffer by several
+    host threads and written in one piece.  md5 of the unmodified reference's output for the same file
+    (oracle/_ref/pairalign -a -n, 90 s on one core; synth.make_random(60, 77, 500, 700))."""
+    import hashlib
+    from phylommand_b200 import synth
+    names, seqs = synth.make_random(60, 77, 500, 700)
+    synth.write_fasta(tmp_path / "big_a.fst", names, seqs)
+    r = subprocess.run([str(exe), "-a", "-n", "big_a.fst"], cwd=tmp_path, capture_output=True, timeout=900)
+    assert r.returncode == 0 and len(r.stdout) == 2587172
+    assert hashlib.md5(r.stdout).hexdigest() == "84fed2463faa907816700626d52cbd8f"
+
+
 def test_product_binary_has_no_double():
     """The double lives under tests/ and the product build never sees it."""
     from phylommand_b200 import build
