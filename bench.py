@@ -62,10 +62,12 @@ KERNELS = {
     "walk_ms": "pa_walk_kernel (statistics of few long pairs: walk over the stored moves of pa_cta_duo_moves_kernel)",
 }
 #: ncu --set full summaries under profiles/ that belong to a workload's dominant kernel (traffic and pipe figures are
-#: only reported when the file for THIS workload exists)
+#: only reported when the file for THIS workload exists); NCU_CELLS: DP cells of the launch a summary was captured on
 NCU_FILES = {"c2": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"], "c3s": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"],
              "c3": ["r02_duo_ncu_full.txt", "r01_v5_duo_bias_ncu_full.txt"], "c5w": ["r01_v4_duo_win_ncu_full.txt"],
              "c2n": ["r02_sets_ncu_full.txt"]}
+
+NCU_CELLS = {"r02_duo_ncu_full.txt": 1123146785408, "r02_sets_ncu_full.txt": 1123146785408}     # both: config 2, one launch
 
 _SETS: dict = {}
 
@@ -276,7 +278,10 @@ def ncu_summary_for(workload_name: str):
         out = {"file": f"profiles/{fn}",
                "alu_pipe_pct": vals.get("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"),
                "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-               "dram_bytes": None, "warp_inst": vals.get("smsp__inst_executed.sum")}
+               "dram_bytes": None, "warp_inst": vals.get("smsp__inst_executed.sum"), "inst_per_cell": None}
+        lanes = vals.get("smsp__thread_inst_executed_per_inst_executed.ratio")
+        if out["warp_inst"] and lanes and fn in NCU_CELLS:       # thread instructions executed per DP cell, everything included
+            out["inst_per_cell"] = out["warp_inst"] * lanes / NCU_CELLS[fn]
         rd, wr = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum")
         if rd is not None and wr is not None:
             out["dram_bytes"] = int(rd + wr)
@@ -457,6 +462,7 @@ def main() -> None:
                "ops_per_cell": OPS_PER_CELL}
         if ncu:
             out["ncu"] = {"file": ncu["file"], "alu_pipe_pct": ncu["alu_pipe_pct"], "issue_active_pct": ncu["issue_active_pct"],
+                          "inst_per_cell": ncu["inst_per_cell"],
                           "note": "from the committed ncu --set full capture of this kernel on this workload's pair shape"}
         return out
 
