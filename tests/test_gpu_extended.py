@@ -2,6 +2,7 @@
 
   * the differential fuzz of tests/test_host_fuzz_vs_reference.py through the real command line (CUDA module)
     against the reference binary that travels in oracle/_ref/;
+  * the pair-FASTA round trip (`-a -n` read back with `--format pairfst`) the same way;
   * CUDA vs oracle on inputs where ties decide everything (repeats, containment, overlapping ends, all-ambiguous);
   * the op strings of two 30 kb pairs against the oracle's 2-bit-move walk (exact parity of -a at config 5 size);
   * one 30 kb x 30 kb and one 30 kb x 400 bp pair, statistics records against the oracle's forward form;
@@ -48,6 +49,35 @@ def test_command_line_fuzz_against_the_reference(cli, tmp_path, seed):
                 if g.exists():
                     g.unlink()
             assert outs[0] == outs[1], (flags, seed)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_pairfasta_round_trip_through_the_cuda_module(cli, tmp_path, seed):
+    """The miniptera.pl pipeline on the GPU: `-a -n` output read back with `--format pairfst`, every
+    step against the reference binary doing the same."""
+    if not REF.exists():
+        pytest.skip("oracle/_ref/pairalign did not travel")
+    from tests import test_host_fuzz_vs_reference as F
+    env = dict(os.environ, PAIRALIGN_DEVICES="0")
+
+    def both(flags, name):
+        outs = []
+        for binary in (REF, cli):
+            r = subprocess.run([str(binary), *flags, name], cwd=tmp_path, capture_output=True, timeout=300, env=env)
+            g = tmp_path / (name + ".alignment_groups")
+            outs.append((r.returncode, r.stdout, g.read_bytes() if g.exists() else None))
+            if g.exists():
+                g.unlink()
+        return outs
+
+    (tmp_path / "in.fst").write_bytes(F.make_case(3000 + seed, group=False).encode())
+    ref, ours = both(["-a", "-n"], "in.fst")
+    assert ours == ref
+    (tmp_path / "pairs.pairfst").write_bytes(ours[1])
+    for flags in (["--format", "pairfst", "-A", "-j", "-n"], ["--format", "pairfst", "-d", "-n"], ["--format", "pairfst", "-p", "-m", "-n"],
+                  ["--format", "pairfst", "-a", "-n"], ["--format", "pairfst", "-g", "alignment_groups"]):
+        r, o = both(flags, "pairs.pairfst")
+        assert o == r, (flags, seed)
 
 
 def test_structured_inputs_on_every_kernel(gpu, oracle):
