@@ -407,6 +407,11 @@ def main() -> None:
             sampler.start()
         el, kern_ms, launches = timed(step_resident, steps, warmup, buckets)
         clocks = sampler.stop() if sampler else None
+        if e2e_steps is None:
+            # the K of the resident timing, capped so that the end-to-end leg of a long step (7 s on the default set at
+            # N = 1) stays within about a minute; el is the max over ranks, so every rank takes the same number
+            per = el / steps
+            e2e_steps = steps if per * steps <= 60.0 else max(3, min(steps, int(60.0 / per)))
         el_e2e, _, _ = timed(step_e2e, e2e_steps, e2e_warmup)
 
         # parity spot check of what was just timed: EVERY rank checks a sample of its own records against the oracle
@@ -429,11 +434,11 @@ def main() -> None:
         del d_out
         res = dict(names=names, seqs=seqs, label=label, total_pairs=total_pairs, total_cells=total_cells, my_cells=my_cells,
                    count=count, masks_bytes=int(masks.nbytes + offsets.nbytes), el=el / steps, kern_ms=kern_ms / steps,
-                   launches=launches, el_e2e=el_e2e / e2e_steps, parts=parts, buckets=buckets, clocks=clocks, ok=ok_all,
+                   launches=launches, el_e2e=el_e2e / e2e_steps, e2e_steps=e2e_steps, parts=parts, buckets=buckets, clocks=clocks, ok=ok_all,
                    cells_rank=cells_rank, kern_rank=[k / steps for k in kern_rank], max_len=int(lens.max()))
         return res
 
-    main_res = measure(args.workload, args.steps, args.warmup, args.steps, max(1, args.warmup // 3), sample_clocks=True)
+    main_res = measure(args.workload, args.steps, args.warmup, None, max(1, args.warmup // 3), sample_clocks=True)
 
     peak = None
     if not args.no_peak:
@@ -530,7 +535,7 @@ def main() -> None:
                        "cells_per_rank": {"min": min(r["cells_rank"]), "max": max(r["cells_rank"])},
                        "kernel_ms_per_rank": {"min": min(r["kern_rank"]), "max": max(r["kern_rank"])},
                        "l2": "256 MiB device write between steps, outside the timed region; the kernel is ALU-bound"},
-            "e2e": {"value": r["total_pairs"] / r["el_e2e"], "unit": "pairs/s", "h2d_bytes_per_step": r["masks_bytes"],
+            "e2e": {"value": r["total_pairs"] / r["el_e2e"], "unit": "pairs/s", "steps": r["e2e_steps"], "h2d_bytes_per_step": r["masks_bytes"],
                     "d2h_bytes_per_step": int(r["count"] * capi.RESULT_DTYPE.itemsize), "ms_per_step": 1e3 * r["el_e2e"],
                     "gcups": r["total_cells"] / r["el_e2e"] / 1e9,
                     "rank0_breakdown_ms_per_call": {k: v / max(1, r["parts"]["calls"]) for k, v in r["parts"].items() if k != "calls"},
