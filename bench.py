@@ -411,7 +411,7 @@ def main() -> None:
             # the K of the resident timing, capped so that the end-to-end leg of a long step (7 s on the default set at
             # N = 1) stays within about a minute; el is the max over ranks, so every rank takes the same number
             per = el / steps
-            e2e_steps = steps if per * steps <= 60.0 else max(3, min(steps, int(60.0 / per)))
+            e2e_steps = steps if per * steps <= 60.0 else min(steps, max(3, int(60.0 / per)))
         el_e2e, _, _ = timed(step_e2e, e2e_steps, e2e_warmup)
 
         # parity spot check of what was just timed: EVERY rank checks a sample of its own records against the oracle
