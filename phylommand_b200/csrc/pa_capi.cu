@@ -167,6 +167,7 @@ struct Context {
     // pa_init brings the devices up on one host thread each: 0 coming up, 1 ready, 2 failed (with its message)
     std::unique_ptr<std::atomic<int>[]> dev_state;
     std::vector<std::string> dev_err;
+    std::vector<int> dev_code;                   // status code that goes with dev_err (PA_ENODEVICE: not an sm_100 part)
     std::vector<std::thread> bringup;
     std::atomic<int> occ_ready{0};               // 1: occ holds the occupancies asked on the first device, 2: that failed
     struct Occ { int duo, duo3, duo8, duo_auto, sets, moves_warp, moves_warp_sets, moves_cta, fast, cta, gen, stats; } occ = {};
@@ -653,8 +654,9 @@ static cudaError_t query_occupancy(Context::Occ &o) {
 static void bring_up_device(Context *c, size_t k) {
     Device &d = c->dev[k];
     char msg[256] = "";
+    int code = PA_ECUDA;
     auto done = [&](bool ok) {
-        if (!ok) c->dev_err[k] = msg;
+        if (!ok) { c->dev_err[k] = msg; c->dev_code[k] = code; }
         if (k == 0) c->occ_ready.store(ok ? 1 : 2, std::memory_order_release);
         c->dev_state[k].store(ok ? 1 : 2, std::memory_order_release);
     };
@@ -665,7 +667,12 @@ static void bring_up_device(Context *c, size_t k) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, d.id);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d.id);
     if (e != cudaSuccess) { snprintf(msg, sizeof msg, "cannot select device %d: %s", d.id, cudaGetErrorString(e)); done(false); return; }
-    if (major < 10) { snprintf(msg, sizeof msg, "device %d is sm_%d%d; this module is built for sm_100a only", d.id, major, minor); done(false); return; }
+    if (major < 10) {
+        snprintf(msg, sizeof msg, "device %d is sm_%d%d; this module is built for sm_100a only", d.id, major, minor);
+        code = PA_ENODEVICE;
+        done(false);
+        return;
+    }
     d.n_sm = n_sm;
     if (k == 0) {
         e = query_occupancy(c->occ);
@@ -714,6 +721,7 @@ int pa_init(const int *devices, int n_dev) {
     c->dev_state.reset(new std::atomic<int>[ids.size()]);
     for (size_t k = 0; k < ids.size(); ++k) c->dev_state[k].store(0);
     c->dev_err.assign(ids.size(), std::string());
+    c->dev_code.assign(ids.size(), PA_OK);
     // Every device on its own host thread, side by side.  Measured on an 8-GPU box (profiles/r02_cli_init_8gpu.txt): the
     // first CUDA call of the process costs ~5 s there whatever follows, a context 0.1-0.4 s; bringing the other devices
     // up in the background while the first one already computes (tried) has nothing to overlap.
@@ -723,9 +731,9 @@ int pa_init(const int *devices, int n_dev) {
     for (size_t k = 0; k < ids.size(); ++k) {
         if (c->dev_state[k].load(std::memory_order_acquire) == 1) continue;
         const std::string msg = c->dev_err[k];
-        const bool wrong_chip = msg.find("sm_100a only") != std::string::npos;
+        const int code = c->dev_code[k];
         destroy_context(c);
-        return fail(wrong_chip ? PA_ENODEVICE : PA_ECUDA, "%s", msg.c_str());
+        return fail(code, "%s", msg.c_str());
     }
     if (const char *f = std::getenv("PAIRALIGN_FORCE_32BIT")) c->force_32bit = (f[0] == '1');
     if (const char *f = std::getenv("PAIRALIGN_KDUO")) c->kduo_forced = std::atoi(f);
